@@ -1,0 +1,13 @@
+"""agnpy_b200: B200-native (sm_100a, FP64) emission-integral hot path of agnpy behind the
+reference's own Python API.  See DESIGN.md / INTEGRATION.md."""
+from .absorption import Absorption
+from .compton import ExternalCompton, SynchrotronSelfCompton
+from .grids import (gamma_e_to_integrate, mu_to_integrate, nu_to_integrate, phi_to_integrate,
+                    trapz_loglog)
+from .synchrotron import Synchrotron
+from .units import Quantity, u
+
+__all__ = ["Synchrotron", "SynchrotronSelfCompton", "ExternalCompton", "Absorption",
+           "trapz_loglog", "gamma_e_to_integrate", "nu_to_integrate", "mu_to_integrate",
+           "phi_to_integrate", "Quantity", "u"]
+__version__ = "0.1.0"

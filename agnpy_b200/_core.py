@@ -1,0 +1,67 @@
+"""Marshalling between numpy (CGS doubles) and the C ABI.  One function per entry point of
+include/agnpy_b200.h, host-pointer flavour: used by the drop-in static methods.  The
+device-pointer flavour is used by agnpy_b200.batch."""
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, hptr, lib
+
+
+def model_row(models, i, *, z=0.0, d_L=1.0, delta_D=1.0, mu_s=1.0, B=0.0, R_b=1.0, ne=None,
+              tgt=()):
+    m = models[i]
+    m["z"], m["d_L"], m["delta_D"], m["mu_s"], m["B"], m["R_b"] = z, d_L, delta_D, mu_s, B, R_b
+    if ne is not None:
+        m["ne"][:] = ne
+    t = np.zeros(8)
+    t[:len(tgt)] = tgt
+    m["tgt"][:] = t
+
+
+def synch_sed_host(models, ne_kind, nu, gamma, ne_table=None, ssa_table=None, ssa=False,
+                   integ=0, want_tau=False):
+    nu, gamma = f64(nu), f64(gamma)
+    n = len(models)
+    sed = np.empty((n, nu.size))
+    tau = np.empty((n, nu.size)) if want_tau else None
+    check(lib().agnpy_b200_synch_sed_host(
+        n, hptr(models), ne_kind, hptr(nu), nu.size, hptr(gamma), gamma.size,
+        hptr(ne_table), hptr(ssa_table), int(bool(ssa)), integ, hptr(sed), hptr(tau)),
+        "agnpy_b200_synch_sed_host")
+    return (sed, tau) if want_tau else sed
+
+
+def ssc_sed_host(models, ne_kind, nu, nu_seed, gamma, ne_table=None, ssa_table=None,
+                 ssa=False, integ=0):
+    nu, nu_seed, gamma = f64(nu), f64(nu_seed), f64(gamma)
+    n = len(models)
+    sed = np.empty((n, nu.size))
+    check(lib().agnpy_b200_ssc_sed_host(
+        n, hptr(models), ne_kind, hptr(nu), nu.size, hptr(nu_seed), nu_seed.size,
+        hptr(gamma), gamma.size, hptr(ne_table), hptr(ssa_table), int(bool(ssa)), integ,
+        hptr(sed)), "agnpy_b200_ssc_sed_host")
+    return sed
+
+
+def ec_sed_host(variant, models, ne_kind, nu, gamma, mu, n_mu, phi, ne_table=None, integ=0):
+    nu, gamma = f64(nu), f64(gamma)
+    mu = None if mu is None else f64(mu)
+    phi = None if phi is None else f64(phi)
+    n = len(models)
+    sed = np.empty((n, nu.size))
+    check(lib().agnpy_b200_ec_sed_host(
+        variant, n, hptr(models), ne_kind, hptr(nu), nu.size, hptr(gamma), gamma.size,
+        hptr(mu), int(n_mu), hptr(phi), 0 if phi is None else phi.size, hptr(ne_table),
+        integ, hptr(sed)), "agnpy_b200_ec_sed_host")
+    return sed
+
+
+def tau_host(variant, models, nu, mu, n_a, phi, l_unit):
+    nu, phi, l_unit = f64(nu), f64(phi), f64(l_unit)
+    mu = None if mu is None else f64(mu)
+    n = len(models)
+    tau = np.empty((n, nu.size))
+    check(lib().agnpy_b200_tau_host(
+        variant, n, hptr(models), hptr(nu), nu.size, hptr(mu), int(n_a), hptr(phi), phi.size,
+        hptr(l_unit), l_unit.size, hptr(tau)), "agnpy_b200_tau_host")
+    return tau

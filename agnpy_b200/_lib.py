@@ -1,0 +1,122 @@
+"""ctypes binding of libagnpy_b200.so (the C ABI of include/agnpy_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing, or there is no
+CUDA device, calls raise.
+"""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libagnpy_b200.so"
+
+# constants of include/agnpy_b200.h
+NE_POWERLAW, NE_BROKEN_POWERLAW, NE_LOG_PARABOLA = 0, 1, 2
+NE_EXP_CUTOFF_POWERLAW, NE_EXP_CUTOFF_BROKEN_POWERLAW, NE_TABLE = 3, 4, 5
+INTEG_TRAPZ, INTEG_LOGLOG = 0, 1
+EC_ISO_MONO, EC_PS_BEHIND_JET, EC_SS_DISK, EC_BLR, EC_DT = 0, 1, 2, 3, 4
+TAU_SS_DISK, TAU_BLR, TAU_DT = 0, 1, 2
+
+EXPORTS = [
+    "agnpy_b200_version", "agnpy_b200_last_error", "agnpy_b200_launch_count",
+    "agnpy_b200_fp64_peak",
+    "agnpy_b200_synch_sed", "agnpy_b200_synch_sed_host",
+    "agnpy_b200_ssc_sed", "agnpy_b200_ssc_sed_host",
+    "agnpy_b200_ec_sed", "agnpy_b200_ec_sed_host",
+    "agnpy_b200_tau", "agnpy_b200_tau_host",
+]
+
+
+class Model(C.Structure):
+    """agnpy_model_t"""
+    _fields_ = [("z", C.c_double), ("d_L", C.c_double), ("delta_D", C.c_double),
+                ("mu_s", C.c_double), ("B", C.c_double), ("R_b", C.c_double),
+                ("ne", C.c_double * 8), ("tgt", C.c_double * 8)]
+
+
+MODEL_DOUBLES = C.sizeof(Model) // 8  # 22
+MODEL_DTYPE = np.dtype([("z", "f8"), ("d_L", "f8"), ("delta_D", "f8"), ("mu_s", "f8"),
+                        ("B", "f8"), ("R_b", "f8"), ("ne", "f8", (8,)), ("tgt", "f8", (8,))])
+assert MODEL_DTYPE.itemsize == C.sizeof(Model)
+
+
+class AgnpyB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (built in-tree by `python agnpy_b200/build.py` /
+    `__graft_entry__.build()`); raises if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise AgnpyB200Error(
+            f"{LIB_PATH} not found: build it with `python agnpy_b200/build.py` "
+            "(agnpy_b200 has no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    dp, ip, vp = C.c_void_p, C.c_int, C.c_void_p
+    L.agnpy_b200_version.restype = C.c_char_p
+    L.agnpy_b200_last_error.restype = C.c_char_p
+    L.agnpy_b200_launch_count.restype = C.c_longlong
+    L.agnpy_b200_fp64_peak.argtypes = [C.c_double, C.POINTER(C.c_double), vp]
+    synch = [ip, dp, ip, dp, ip, dp, ip, dp, dp, ip, ip, dp, dp]
+    L.agnpy_b200_synch_sed.argtypes = synch + [vp]
+    L.agnpy_b200_synch_sed_host.argtypes = synch
+    ssc = [ip, dp, ip, dp, ip, dp, ip, dp, ip, dp, dp, ip, ip, dp]
+    L.agnpy_b200_ssc_sed.argtypes = ssc + [vp]
+    L.agnpy_b200_ssc_sed_host.argtypes = ssc
+    ec = [ip, ip, dp, ip, dp, ip, dp, ip, dp, ip, dp, ip, dp, ip, dp]
+    L.agnpy_b200_ec_sed.argtypes = ec + [vp]
+    L.agnpy_b200_ec_sed_host.argtypes = ec
+    tau = [ip, ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
+    L.agnpy_b200_tau.argtypes = tau + [vp]
+    L.agnpy_b200_tau_host.argtypes = tau
+    for name in EXPORTS[3:]:
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().agnpy_b200_last_error().decode()
+        raise AgnpyB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().agnpy_b200_launch_count())
+
+
+def fp64_peak(ms=200.0, stream=None):
+    """measured FP64 FMA peak of the current device in FLOP/s"""
+    out = C.c_double(0.0)
+    check(lib().agnpy_b200_fp64_peak(float(ms), C.byref(out), stream), "fp64_peak")
+    return out.value
+
+
+# ---- helpers to pass numpy arrays / torch tensors ------------------------------------------
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def hptr(a):
+    """host pointer of a contiguous float64 / model ndarray (or None)"""
+    return None if a is None else a.ctypes.data
+
+
+def dptr(t):
+    """device pointer of a contiguous CUDA torch tensor (or None)"""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise AgnpyB200Error("device entry points need contiguous CUDA tensors")
+    return t.data_ptr()
+
+
+def make_models(n):
+    return np.zeros(n, dtype=MODEL_DTYPE)

@@ -1,0 +1,211 @@
+// Shared device functions for the agnpy_b200 emission-integral kernels (sm_100a, FP64).
+//
+// The whole library is compiled with -fmad=false: every a*b+c written with plain operators
+// is rounded twice exactly like numpy does, so mask operands (gamma >= gamma_min,
+// gamma_min <= gamma/delta_D <= gamma_max, s < 1, ...) are bit-identical to the reference's.
+// FMAs are used only where written explicitly (fma()) inside the hot accumulation loops.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/agnpy_b200.h"
+
+namespace agb {
+
+// ---- constants: astropy>=7 (CODATA 2018) in CGS; literals are the repr() of the doubles the
+// ---- reference computes (agnpy/utils/conversion.py:1-9, agnpy/synchrotron/synchrotron.py:12)
+constexpr double kC = 29979245800.0;
+constexpr double kH = 6.62607015e-27;
+constexpr double kMe = 9.1093837015e-28;
+constexpr double kE = 4.803204712570263e-10;
+constexpr double kSigmaT = 6.6524587321e-25;
+constexpr double kG = 6.6743e-08;
+constexpr double kMsun = 1.988409870698051e+33;
+constexpr double kMec2 = 8.187105776823886e-07;   // m_e * c**2
+constexpr double kLambdaC = 2.426310238683092e-10; // h / (m_e c)
+constexpr double kPi = 3.141592653589793;
+constexpr double kTiny = 2.2250738585072014e-308;
+constexpr double kFmax = 1.7976931348623157e+308;
+
+// ---- small helpers -------------------------------------------------------------------------
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// utils/math.py:49-52  log(clip(x, tiny, fmax)); NaN propagates like np.clip
+__device__ __forceinline__ double clipped_log(double x) {
+    double v = x;
+    if (v < kTiny) v = kTiny;
+    if (v > kFmax) v = kFmax;
+    return log(v);
+}
+
+// nu -> dimensionless energy in a frame (z, delta_D): conversion.py:30-35
+__device__ __forceinline__ double nu_to_eps(double nu, double z, double delta_D) {
+    double e0 = kH * nu / kMec2;
+    return (1.0 + z) * e0 / delta_D;
+}
+
+// spectra.py:210-225: value of the (possibly snapped) k-th grid point
+__device__ __forceinline__ double snapped(double g, int k, int n, double g0, double gN,
+                                          double gmin, double gmax) {
+    // g0 / gN are the unsnapped first / last grid values
+    if (k == 0 && gmin > g0 && (gmin - g0) / g0 < 1e-10) return gmin;
+    if (k == n - 1 && gN > gmax && (gN - gmax) / gmax < 1e-10) return gmax;
+    return g;
+}
+
+// ---- electron distributions: spectra.py static evaluate() of the five analytic shapes --------
+// par layout = the reference's `parameters` order (see include/agnpy_b200.h)
+__device__ __forceinline__ void ne_bounds(int kind, const double* p, double& gmin, double& gmax) {
+    switch (kind) {
+        case AGNPY_NE_POWERLAW: gmin = p[2]; gmax = p[3]; break;
+        case AGNPY_NE_BROKEN_POWERLAW: gmin = p[4]; gmax = p[5]; break;
+        case AGNPY_NE_LOG_PARABOLA: gmin = p[4]; gmax = p[5]; break;
+        case AGNPY_NE_EXP_CUTOFF_POWERLAW: gmin = p[3]; gmax = p[4]; break;
+        default: gmin = p[5]; gmax = p[6]; break;  // EXP_CUTOFF_BROKEN_POWERLAW
+    }
+}
+
+__device__ inline double ne_eval(int kind, const double* p, double g) {
+    double gmin, gmax;
+    ne_bounds(kind, p, gmin, gmax);
+    if (!((gmin <= g) && (g <= gmax))) return 0.0;
+    switch (kind) {
+        case AGNPY_NE_POWERLAW:  // spectra.py:272-277
+            return p[0] * pow(g, -p[1]);
+        case AGNPY_NE_BROKEN_POWERLAW: {  // :366-374
+            double idx = (g <= p[3]) ? p[1] : p[2];
+            return p[0] * pow(g / p[3], -idx);
+        }
+        case AGNPY_NE_LOG_PARABOLA: {  // :470-479
+            double ratio = g / p[3];
+            double idx = -p[1] - p[2] * log10(ratio);
+            return p[0] * pow(ratio, idx);
+        }
+        case AGNPY_NE_EXP_CUTOFF_POWERLAW:  // :569-576
+            return p[0] * pow(g, -p[1]) * exp(-g / p[2]);
+        default: {  // EXP_CUTOFF_BROKEN_POWERLAW :673-681  (k,p1,p2,gamma_c,gamma_b,..)
+            double idx = (g <= p[4]) ? p[1] : p[2];
+            return p[0] * pow(g / p[4], -idx) * exp(-g / p[3]);
+        }
+    }
+}
+
+// gamma^2 d/dgamma(n_e/gamma^2): spectra.py:282-290, 387-396, 492-499, 583-591, 695-710
+__device__ inline double ne_ssa(int kind, const double* p, double g) {
+    double gmin, gmax;
+    ne_bounds(kind, p, gmin, gmax);
+    if (!((gmin <= g) && (g <= gmax))) return 0.0;
+    switch (kind) {
+        case AGNPY_NE_POWERLAW:
+            return p[0] * (-(p[1] + 2.0) * pow(g, -p[1] - 1.0));
+        case AGNPY_NE_BROKEN_POWERLAW: {
+            double idx = (g <= p[3]) ? p[1] : p[2];
+            return p[0] * -(idx + 2.0) / g * pow(g / p[3], -idx);
+        }
+        case AGNPY_NE_LOG_PARABOLA: {
+            double pref = -(p[1] + 2.0 * p[2] * log10(g / p[3]) + 2.0) / g;
+            return pref * ne_eval(kind, p, g);
+        }
+        case AGNPY_NE_EXP_CUTOFF_POWERLAW: {
+            double pref = -(p[1] + 2.0) / g + (-1.0 / p[2]);
+            return pref * ne_eval(kind, p, g);
+        }
+        default: {
+            double idx = (g <= p[4]) ? p[1] : p[2];
+            double pref = -(idx + 2.0) / g + (-1.0 / p[3]);
+            return pref * ne_eval(kind, p, g);
+        }
+    }
+}
+
+// ---- integration rules -------------------------------------------------------------------
+// numpy.trapz as a fixed weighted sum: w_0=(x1-x0)/2, w_k=(x_{k+1}-x_{k-1})/2, w_{n-1}=...
+__device__ __forceinline__ double trapz_weight(const double* x, int k, int n) {
+    if (n < 2) return 0.0;
+    double lo = x[k > 0 ? k - 1 : 0];
+    double hi = x[k < n - 1 ? k + 1 : n - 1];
+    return (hi - lo) * 0.5;
+}
+
+// one interval of utils/math.py:55-119 (trapz_loglog); ly_* are clipped logs of y_*
+__device__ __forceinline__ double loglog_interval(double x_lo, double x_up, double y_lo,
+                                                  double y_up, double ly_lo, double ly_up) {
+    if (y_lo == 0.0 || y_up == 0.0 || x_lo == x_up) return 0.0;  // :112-117
+    double m = (ly_lo - ly_up) / (clipped_log(x_lo) - clipped_log(x_up));  // :104
+    double m1 = m + 1.0;
+    if (fabs(m1) > 1e-10)  // :106-110
+        return y_lo / m1 * (x_up * pow(x_up / x_lo, m) - x_lo);
+    return x_lo * y_lo * clipped_log(x_up / x_lo);
+}
+
+// same interval with the per-interval constants precomputed: inv_dlx = 1/(ln x_lo - ln x_up),
+// lr = ln(x_up/x_lo); pow(r, m) is evaluated as exp(m*lr)
+__device__ __forceinline__ double loglog_interval_pre(double x_lo, double x_up, double inv_dlx,
+                                                      double lr, double y_lo, double y_up,
+                                                      double ly_lo, double ly_up) {
+    if (y_lo == 0.0 || y_up == 0.0 || x_lo == x_up) return 0.0;
+    double m = (ly_lo - ly_up) * inv_dlx;
+    double m1 = m + 1.0;
+    if (fabs(m1) > 1e-10) return y_lo / m1 * (x_up * exp(m * lr) - x_lo);
+    return x_lo * y_lo * lr;
+}
+
+// ---- reductions ------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0. `red` needs >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
+// synchrotron.py:16-24 R(x) (Aharonian et al. 2010 D7); x^(1/3) via cbrt
+__device__ __forceinline__ double R_synch(double x) {
+    double x13 = cbrt(x);
+    double x23 = x13 * x13;
+    double x43 = x23 * x23;
+    double t1 = 1.808 * x13 / sqrt(1.0 + 3.4 * x23);
+    double t2n = 1.0 + 2.21 * x23 + 0.347 * x43;
+    double t2d = 1.0 + 1.353 * x23 + 0.217 * x43;
+    return t1 * t2n / t2d * exp(-x);
+}
+
+// synchrotron.py:64-68 attenuation 3u/tau, u = 1/2 + e^-t/t - (1-e^-t)/t^2.  The reference
+// formula cancels catastrophically for small tau (abs. error ~ ulp/tau^2); it is evaluated
+// here through its series u = sum_{n>=1} (-1)^(n+1) t^n (n+1)/(n+2)! for tau < 0.5.
+__device__ __forceinline__ double ssa_attenuation(double tau) {
+    if (tau < 1e-3) return 1.0;
+    if (tau < 0.5) {
+        double term = tau / 2.0;  // t^n/(n+1)!  for n=1
+        double u = 0.0, sgn = 1.0;
+        for (int n = 1; n <= 24; ++n) {
+            // coefficient (n+1)/(n+2)! = [1/(n+1)!] * (n+1)/(n+2)
+            u += sgn * term * (double)(n + 1) / (double)(n + 2);
+            term = term * tau / (double)(n + 2);
+            sgn = -sgn;
+        }
+        return 3.0 * u / tau;
+    }
+    double e = exp(-tau);
+    double u = 0.5 + e / tau - (1.0 - e) / (tau * tau);
+    return 3.0 * u / tau;
+}
+
+// launch bookkeeping shared by all translation units (defined in runtime.cu)
+void note_launch(int n = 1);
+void* workspace(size_t bytes, cudaStream_t stream);
+int fail(int code, const char* what);
+int check_last(const char* what);
+
+}  // namespace agb

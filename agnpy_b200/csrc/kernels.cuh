@@ -1,0 +1,31 @@
+// Host-side launchers of the kernel families (definitions in synch_ssc.cu, ec.cu, tau.cu).
+#pragma once
+#include "common.cuh"
+
+namespace agb {
+
+void launch_prep_gamma(const agnpy_model_t* models, int n_models, int ne_kind, const double* gamma,
+                       int n_gamma, const double* ne_table, const double* ssa_table, int mode,
+                       double* tab, cudaStream_t stream);
+
+int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
+                 const double* tab, int n_gamma, int ssa, int integ, int out_mode, double* out,
+                 double* tau_out, double* eps_out, cudaStream_t stream);
+
+int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
+               const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,
+               int n_seed, int integ, double* out, cudaStream_t stream);
+
+// bytes of scratch the EC / tau pipelines need for `n_models` models
+size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi);
+int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, const double* nu,
+           int n_nu, const double* gamma, int n_gamma, const double* mu, int n_mu,
+           const double* phi, int n_phi, const double* ne_table, int integ, double* sed,
+           double* ws, cudaStream_t stream);
+
+size_t tau_workspace_bytes(int variant, int n_models, int n_nu, int n_a, int n_phi, int n_l);
+int run_tau(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
+            const double* mu, int n_a, const double* phi, int n_phi, const double* l_unit, int n_l,
+            double* tau, double* ws, cudaStream_t stream);
+
+}  // namespace agb

@@ -1,0 +1,124 @@
+// Library runtime: error text, launch counter, stream-keyed workspace cache, FP64-peak probe.
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+
+#include "common.cuh"
+
+namespace agb {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int fail(int code, const char* what) {
+    g_err = what ? what : "";
+    return code;
+}
+
+int check_last(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return AGNPY_OK;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return AGNPY_ERR_CUDA;
+}
+
+// One growing scratch buffer per (device, stream).  Work on one stream is ordered, so a
+// buffer can be reused by consecutive calls on that stream; growing it synchronises the
+// stream first (rare: sizes are stable inside a fit loop).
+struct Slot {
+    void* ptr = nullptr;
+    size_t size = 0;
+};
+static std::mutex g_ws_mutex;
+static std::map<std::pair<int, cudaStream_t>, Slot> g_ws;
+
+void* workspace(size_t bytes, cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Slot& s = g_ws[{dev, stream}];
+    if (s.size >= bytes) return s.ptr;
+    if (s.ptr) {
+        cudaStreamSynchronize(stream);
+        cudaFree(s.ptr);
+        s.ptr = nullptr;
+        s.size = 0;
+    }
+    size_t want = bytes + bytes / 4 + (1u << 20);
+    if (cudaMalloc(&s.ptr, want) != cudaSuccess) {
+        cudaGetLastError();
+        s.ptr = nullptr;
+        return nullptr;
+    }
+    s.size = want;
+    return s.ptr;
+}
+
+// ---- FP64 peak probe: 8 independent DFMA chains per thread, all SMs full -------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace agb
+
+extern "C" {
+
+const char* agnpy_b200_version(void) { return "agnpy_b200 0.1.0 (sm_100a)"; }
+const char* agnpy_b200_last_error(void) { return agb::g_err.c_str(); }
+long long agnpy_b200_launch_count(void) { return agb::g_launches.load(); }
+
+int agnpy_b200_fp64_peak(double ms, double* flops_per_s, void* stream_) {
+    using namespace agb;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(AGNPY_ERR_CUDA, "no CUDA device");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* out = (double*)workspace(64, stream);
+    if (!out) return fail(AGNPY_ERR_NOMEM, "workspace");
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int iters = 2000;
+    float t = 0.f;
+    double best = 0.0;
+    double spent = 0.0;
+    // warm-up + calibrate, then repeat until `ms` of device time has been spent
+    for (int rep = 0; rep < 64; ++rep) {
+        cudaEventRecord(e0, stream);
+        fp64_peak_kernel<<<blocks, threads, 0, stream>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, stream);
+        note_launch();
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        cudaEventElapsedTime(&t, e0, e1);
+        double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        if (rep > 0) {
+            double rate = flops / (t * 1e-3);
+            if (rate > best) best = rate;
+            spent += t;
+        }
+        if (t < 2.0f) iters *= 2;
+        if (spent >= ms) break;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (int rc = check_last("fp64_peak")) return rc;
+    *flops_per_s = best;
+    return AGNPY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+"""Default integration grids and integrator selection (agnpy/utils/math.py:6-9, 55-119)."""
+import numpy as np
+
+from . import _lib
+
+gamma_e_to_integrate = np.logspace(1, 9, 200)   # utils/math.py:6
+nu_to_integrate = np.logspace(5, 30, 200)        # utils/math.py:7  [Hz]
+mu_to_integrate = np.linspace(-1, 1, 100)        # utils/math.py:8
+phi_to_integrate = np.linspace(0, 2 * np.pi, 50) # utils/math.py:9
+
+
+def trapz_loglog(*args, **kwargs):
+    """Selector for the device-side log-log trapezoidal rule (utils/math.py:55-119).
+    Pass it as `integrator=`; the integration itself happens inside the CUDA kernels."""
+    raise NotImplementedError(
+        "agnpy_b200.trapz_loglog only selects the device integrator; it is not a host function")
+
+
+_TRAPZ_NAMES = {"trapz", "trapezoid"}
+
+
+def integrator_code(integrator):
+    """`integrator=` keyword -> AGNPY_INTEG_*.  Accepts numpy.trapz / numpy.trapezoid, the
+    reference's or this package's `trapz_loglog`, or the strings "trapz" / "trapz_loglog".
+    Anything else raises: there is no host fallback that could run an arbitrary callable."""
+    if integrator is None:
+        return _lib.INTEG_TRAPZ
+    name = integrator if isinstance(integrator, str) else getattr(integrator, "__name__", "")
+    if name in _TRAPZ_NAMES:
+        return _lib.INTEG_TRAPZ
+    if name == "trapz_loglog":
+        return _lib.INTEG_LOGLOG
+    raise ValueError(
+        f"unsupported integrator {integrator!r}: use numpy.trapz or trapz_loglog")
+
+
+def as_grid(x, name, ascending=True):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    if a.size < 2:
+        raise ValueError(f"{name}: need at least 2 grid points")
+    if ascending and not np.all(np.diff(a) > 0):
+        raise ValueError(f"{name}: grid must be strictly ascending")
+    return a

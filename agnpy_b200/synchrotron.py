@@ -1,0 +1,78 @@
+"""Drop-in for agnpy/synchrotron/synchrotron.py: `Synchrotron` with the reference's static
+`evaluate_sed_flux` / `evaluate_tau_ssa` signatures (synchrotron.py:101-144), running on the
+fused FP64 CUDA kernel K1."""
+import numpy as np
+
+from . import _core, _lib, spectra
+from .grids import as_grid, gamma_e_to_integrate, integrator_code
+from .units import strip, wrap
+
+__all__ = ["Synchrotron"]
+
+
+def _blob_models(z, d_L, delta_D, B, R_b, ne_par):
+    models = _lib.make_models(1)
+    _core.model_row(models, 0, z=float(z), d_L=strip(d_L, "cm", "d_L"), delta_D=float(delta_D),
+                    B=strip(B, "G", "B"), R_b=strip(R_b, "cm", "R_b"), ne=ne_par)
+    return models
+
+
+def _ne_setup(n_e, args, gamma, ssa):
+    """kind, parameters, the gamma grid to upload and (for interpolated n_e) the tables"""
+    kind, par = spectra.describe(n_e, args)
+    gamma = as_grid(gamma, "gamma")
+    ne_table = ssa_table = None
+    if kind == _lib.NE_TABLE:
+        g = spectra.snap_boundaries(gamma, par[1], par[2])
+        ne_table, ssa_table = spectra.tables(n_e, args, g, ssa)
+    return kind, par, gamma, ne_table, ssa_table
+
+
+class Synchrotron:
+    """synchrotron.py:71-277.  `blob` is any object exposing z, d_L, delta_D, B, R_b, n_e
+    (with `.parameters`) and gamma_e, e.g. an agnpy Blob."""
+
+    def __init__(self, blob, ssa=False, integrator=np.trapezoid):
+        self.blob = blob
+        self.ssa = ssa
+        self.integrator = integrator
+
+    @staticmethod
+    def evaluate_tau_ssa(nu, z, d_L, delta_D, B, R_b, n_e, *args, integrator=np.trapezoid,
+                         gamma=gamma_e_to_integrate):
+        """SSA optical depth, synchrotron.py:101-129; returns a plain ndarray."""
+        nu_hz = strip(nu, "Hz", "nu")
+        kind, par, gamma, ne_t, ssa_t = _ne_setup(n_e, args, gamma, True)
+        models = _blob_models(z, d_L, delta_D, B, R_b, par)
+        _, tau = _core.synch_sed_host(models, kind, np.ravel(nu_hz), gamma, ne_t, ssa_t, True,
+                                      integrator_code(integrator), want_tau=True)
+        return tau[0].reshape(np.shape(nu_hz))
+
+    @staticmethod
+    def evaluate_sed_flux(nu, z, d_L, delta_D, B, R_b, n_e, *args, ssa=False,
+                          integrator=np.trapezoid, gamma=gamma_e_to_integrate):
+        """nu F_nu [erg cm-2 s-1] of synchrotron radiation, synchrotron.py:131-211."""
+        nu_hz = strip(nu, "Hz", "nu")
+        kind, par, gamma, ne_t, ssa_t = _ne_setup(n_e, args, gamma, ssa)
+        models = _blob_models(z, d_L, delta_D, B, R_b, par)
+        sed = _core.synch_sed_host(models, kind, np.ravel(nu_hz), gamma, ne_t, ssa_t, ssa,
+                                   integrator_code(integrator))
+        return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
+
+    def sed_flux(self, nu):
+        """synchrotron.py:229-244"""
+        b = self.blob
+        return self.evaluate_sed_flux(nu, b.z, b.d_L, b.delta_D, b.B, b.R_b, b.n_e,
+                                      *b.n_e.parameters, ssa=self.ssa,
+                                      integrator=self.integrator, gamma=b.gamma_e)
+
+    def sed_luminosity(self, nu):
+        """synchrotron.py:259-265"""
+        d_L = strip(self.blob.d_L, "cm", "d_L")
+        return wrap(4 * np.pi * d_L**2 * strip(self.sed_flux(nu), "erg cm-2 s-1"), "erg s-1")
+
+    def sed_peak_flux(self, nu):
+        return self.sed_flux(nu).max()
+
+    def sed_peak_nu(self, nu):
+        return nu[self.sed_flux(nu).argmax()]

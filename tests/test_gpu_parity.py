@@ -1,0 +1,331 @@
+"""GPU parity: the CUDA path (through the drop-in Python API -> host C ABI) against the CPU
+oracle on identical grids.  Bar (BASELINE.json north_star): rtol 1e-9 in FP64, exact zeros
+where the oracle is exactly zero (SURVEY.md 8(d) "Parity check")."""
+import numpy as np
+import pytest
+
+import agnpy_b200 as ab
+from agnpy_b200 import spectra, u
+from oracle import agnpy_oracle as orc
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+NE_CASES = {
+    "PowerLaw": (1e-7, 2.8, 1e2, 1e6),
+    "BrokenPowerLaw": (1e-8, 1.9, 2.6, 1e4, 10.0, 1e6),
+    "LogParabola": (1e-3, 2.0, 0.4, 1e4, 2.0, 1e6),
+    "ExpCutoffPowerLaw": (1e-8, 2.1, 3e4, 10.0, 1e6),
+    "ExpCutoffBrokenPowerLaw": (1e-8, 1.8, 2.9, 2e5, 1e4, 10.0, 1e6),
+}
+
+
+def ne_obj(kind, args):
+    return getattr(spectra, kind)(*args)
+
+
+def q_args(args):
+    return (args[0] * u.Unit("cm-3"),) + tuple(args[1:])
+
+
+def assert_parity(gpu, ref, rtol=RTOL, what=""):
+    gpu, ref = np.asarray(gpu, float), np.asarray(ref, float)
+    assert gpu.shape == ref.shape
+    assert np.all(np.isfinite(gpu) == np.isfinite(ref)), what
+    dev, zeros_ok = cases.max_rel_dev(gpu, ref)
+    assert zeros_ok, f"{what}: non-zero where the oracle is exactly zero"
+    assert dev <= rtol, f"{what}: max rel dev {dev:.3e} > {rtol}"
+    assert np.count_nonzero(ref) > 0, f"{what}: degenerate case (oracle all zero)"
+
+
+def stable_attenuation(tau):
+    """3u/tau of synchrotron.py:64-68 evaluated without cancellation (series for tau<0.5)"""
+    tau = np.asarray(tau, float)
+    out = np.ones_like(tau)
+    small = (tau >= 1e-3) & (tau < 0.5)
+    t = tau[small]
+    term, acc, sgn = t / 2, np.zeros_like(t), 1.0
+    for n in range(1, 25):
+        acc = acc + sgn * term * (n + 1) / (n + 2)
+        term = term * t / (n + 2)
+        sgn = -sgn
+    out[small] = 3 * acc / t
+    big = tau >= 0.5
+    t = tau[big]
+    out[big] = 3 * (0.5 + np.exp(-t) / t - (1 - np.exp(-t)) / t**2) / t
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 synchrotron
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", list(NE_CASES))
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+def test_synch_all_distributions(kind, integ):
+    args = NE_CASES[kind]
+    nu = np.logspace(8, 24, 80)
+    gamma = np.logspace(np.log10(args[-2]), np.log10(args[-1]), 200)
+    ref = orc.synch_sed_flux(nu, 0.069, 1e27, 10.0, 1.0, 1e16, kind, args, integrator=integ,
+                             gamma=gamma)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.Synchrotron.evaluate_sed_flux(
+        nu * u.Hz, 0.069, 1e27 * u.cm, 10.0, 1.0 * u.G, 1e16 * u.cm, ne_obj(kind, args),
+        *q_args(args), integrator=integrator, gamma=gamma)
+    assert got.unit == u.Unit("erg cm-2 s-1")
+    assert_parity(got.value, ref, what=f"synch {kind} {integ}")
+
+
+@pytest.mark.parametrize("kind", ["PowerLaw", "BrokenPowerLaw", "LogParabola",
+                                  "ExpCutoffPowerLaw", "ExpCutoffBrokenPowerLaw"])
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+def test_synch_ssa(kind, integ):
+    """tau_ssa to 1e-9; the attenuated SED against the cancellation-free attenuation of the
+    oracle's tau (the reference's 3u/tau loses ~ulp/tau^2 for small tau)."""
+    shape = {"PowerLaw": (2, 2, 1e6), "BrokenPowerLaw": (2, 3, 1e4, 2, 1e6),
+             "LogParabola": (2, 0.4, 1e4, 2, 1e6), "ExpCutoffPowerLaw": (2, 1e5, 2, 1e6),
+             "ExpCutoffBrokenPowerLaw": (2, 3, 1e5, 1e4, 2, 1e6)}[kind]
+    k = orc.ne_norm_from_total_density(kind, 1e2, *shape)
+    args = (k,) + shape
+    nu = np.logspace(8, 20, 70)
+    gamma = np.logspace(np.log10(2), 6, 200)
+    d_L = cases.lum_dist_cm(0.1)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    tau_ref = orc.synch_tau_ssa(nu, 0.1, d_L, 10, 0.1, 5e15, kind, args, integrator=integ, gamma=gamma)
+    tau = ab.Synchrotron.evaluate_tau_ssa(nu * u.Hz, 0.1, d_L * u.cm, 10, 0.1 * u.G, 5e15 * u.cm,
+                                          ne_obj(kind, args), *q_args(args),
+                                          integrator=integrator, gamma=gamma)
+    assert_parity(tau, tau_ref, what=f"tau_ssa {kind} {integ}")
+    thin = orc.synch_sed_flux(nu, 0.1, d_L, 10, 0.1, 5e15, kind, args, integrator=integ, gamma=gamma)
+    got = ab.Synchrotron.evaluate_sed_flux(nu * u.Hz, 0.1, d_L * u.cm, 10, 0.1 * u.G, 5e15 * u.cm,
+                                           ne_obj(kind, args), *q_args(args), ssa=True,
+                                           integrator=integrator, gamma=gamma)
+    assert_parity(got.value, thin * stable_attenuation(tau_ref), what=f"ssa sed {kind} {integ}")
+    # and against the reference formula itself, with its own conditioning as tolerance
+    ref = orc.synch_sed_flux(nu, 0.1, d_L, 10, 0.1, 5e15, kind, args, ssa=True, integrator=integ,
+                             gamma=gamma)
+    tol = RTOL + 20 * np.finfo(float).eps / np.maximum(tau_ref, 1e-3) ** 3
+    assert np.all(np.abs(got.value / ref - 1) <= tol)
+
+
+def test_synch_default_gamma_and_snap():
+    """default grid logspace(1,9,200) and the boundary snap of spectra.py:210-225: a grid
+    whose ends miss [gamma_min, gamma_max] by rounding must not lose its end points."""
+    args = (1e-8, 2.3, 10.0, 1e6)
+    gamma = np.logspace(1, 6, 200)
+    gamma[0] = np.nextafter(10.0, 0)      # just below gamma_min
+    gamma[-1] = np.nextafter(1e6, 2e6)    # just above gamma_max
+    nu = np.logspace(9, 20, 40)
+    ref = orc.synch_sed_flux(nu, 0.05, 1e27, 12.0, 0.3, 2e16, "PowerLaw", args, gamma=gamma)
+    got = ab.Synchrotron.evaluate_sed_flux(nu * u.Hz, 0.05, 1e27 * u.cm, 12.0, 0.3 * u.G,
+                                           2e16 * u.cm, spectra.PowerLaw(*args), *q_args(args),
+                                           gamma=gamma)
+    assert_parity(got.value, ref, what="synch snap")
+    ref = orc.synch_sed_flux(nu, 0.05, 1e27, 12.0, 0.3, 2e16, "PowerLaw", args)
+    got = ab.Synchrotron.evaluate_sed_flux(nu * u.Hz, 0.05, 1e27 * u.cm, 12.0, 0.3 * u.G,
+                                           2e16 * u.cm, spectra.PowerLaw(*args), *q_args(args))
+    assert_parity(got.value, ref, what="synch default gamma")
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 SSC  (BASELINE config 1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+@pytest.mark.parametrize("ssa", [False, True])
+def test_ssc_config1(integ, ssa):
+    c = cases.case_c1()
+    ref = orc.ssc_sed_flux(c["nu"], c["z"], c["d_L"], c["delta_D"], c["B"], c["R_b"], c["ne_kind"],
+                           c["ne_args"], ssa=ssa, integrator=integ, gamma=c["gamma"])
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.SynchrotronSelfCompton.evaluate_sed_flux(
+        c["nu"] * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["B"] * u.G, c["R_b"] * u.cm,
+        ne_obj(c["ne_kind"], c["ne_args"]), *q_args(c["ne_args"]), ssa=ssa,
+        integrator=integrator, gamma=c["gamma"])
+    # with SSA the seed spectrum carries the reference's ill-conditioned attenuation
+    rtol = RTOL if not ssa else 1e-6
+    assert_parity(got.value, ref, rtol=rtol, what=f"ssc {integ} ssa={ssa}")
+
+
+@pytest.mark.parametrize("kind", list(NE_CASES))
+def test_ssc_all_distributions(kind):
+    args = NE_CASES[kind]
+    nu = np.logspace(12, 28, 50)
+    gamma = np.logspace(np.log10(args[-2]), np.log10(args[-1]), 150)
+    ref = orc.ssc_sed_flux(nu, 0.069, 1e27, 10.0, 1.0, 1e16, kind, args, gamma=gamma)
+    got = ab.SynchrotronSelfCompton.evaluate_sed_flux(
+        nu * u.Hz, 0.069, 1e27 * u.cm, 10.0, 1.0 * u.G, 1e16 * u.cm, ne_obj(kind, args),
+        *q_args(args), gamma=gamma)
+    assert_parity(got.value, ref, what=f"ssc {kind}")
+
+
+def test_ssc_on_the_seed_grid():
+    """output frequencies identical to the seed grid: eps_s == eps_j rows sit exactly on
+    the q == q_min mask boundary, which must be decided as numpy decides it."""
+    c = cases.case_c1()
+    nu = orc.default_nu_seed()[60:160:3]
+    ref = orc.ssc_sed_flux(nu, c["z"], c["d_L"], c["delta_D"], c["B"], c["R_b"], c["ne_kind"],
+                           c["ne_args"], gamma=c["gamma"])
+    got = ab.SynchrotronSelfCompton.evaluate_sed_flux(
+        nu * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["B"] * u.G, c["R_b"] * u.cm,
+        ne_obj(c["ne_kind"], c["ne_args"]), *q_args(c["ne_args"]), gamma=c["gamma"])
+    assert_parity(got.value, ref, what="ssc on seed grid")
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 external Compton
+# ---------------------------------------------------------------------------------------------
+def ec_args(c):
+    return (c["nu"] * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["mu_s"], c["R_b"] * u.cm)
+
+
+def ne_tail(c):
+    return (ne_obj(c["ne_kind"], c["ne_args"]),) + q_args(c["ne_args"])
+
+
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+@pytest.mark.parametrize("r", [1e16, 2e17, 1e18])
+def test_ec_blr(integ, r):
+    c = cases.case_c2(n_nu=40, r=r)
+    ref = cases.ORACLE_EC["blr"](c, integ)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.ExternalCompton.evaluate_sed_flux_blr(
+        *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_line"], c["epsilon_line"],
+        c["R_line"] * u.cm, c["r"] * u.cm, *ne_tail(c), integrator=integrator, gamma=c["gamma"],
+        mu=c["mu"], phi=c["phi"])
+    assert_parity(got.value, ref, what=f"ec blr {integ} r={r:g}")
+
+
+def test_ec_blr_config2_full_size():
+    """BASELINE config 2 at full size: 200 nu x 200 gamma x 100 mu x 50 phi"""
+    c = cases.case_c2()
+    ref = np.concatenate([cases.ORACLE_EC["blr"](dict(c, nu=c["nu"][i:i + 25]))
+                          for i in range(0, 200, 25)])
+    got = ab.ExternalCompton.evaluate_sed_flux_blr(
+        *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_line"], c["epsilon_line"],
+        c["R_line"] * u.cm, c["r"] * u.cm, *ne_tail(c), gamma=c["gamma"], mu=c["mu"], phi=c["phi"])
+    assert_parity(got.value, ref, what="ec blr config 2")
+
+
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+@pytest.mark.parametrize("r", [1e18, 1e20])
+def test_ec_dt(integ, r):
+    c = cases.case_c3_dt(n_nu=80, r=r)
+    ref = cases.ORACLE_EC["dt"](c, integ)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.ExternalCompton.evaluate_sed_flux_dt(
+        *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_dt"], c["epsilon_dt"],
+        c["R_dt"] * u.cm, c["r"] * u.cm, *ne_tail(c), integrator=integrator, gamma=c["gamma"],
+        phi=c["phi"])
+    assert_parity(got.value, ref, what=f"ec dt {integ} r={r:g}")
+
+
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+@pytest.mark.parametrize("r", [1e17, 1e18])
+def test_ec_ss_disk(integ, r):
+    c = cases.case_disk(n_nu=40, r=r)
+    ref = cases.ORACLE_EC["ss_disk"](c, integ)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.ExternalCompton.evaluate_sed_flux_ss_disk(
+        *ec_args(c), c["M_BH"] * u.g, c["L_disk"] * u.Unit("erg s-1"), c["eta"], c["R_in"] * u.cm,
+        c["R_out"] * u.cm, c["r"] * u.cm, *ne_tail(c), integrator=integrator, gamma=c["gamma"],
+        mu_size=c["mu_size"], phi=c["phi"])
+    assert_parity(got.value, ref, what=f"ec disk {integ} r={r:g}")
+
+
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+def test_ec_iso_mono_cmb(integ):
+    b = cases.blob_ec()
+    nu = np.logspace(15, 29, 40)
+    u_0 = 7.5657e-15 * 2.72548**4 * (1 + b["z"]) ** 4
+    eps_0 = 2.7 * orc.K_B * 2.72548 / orc.MEC2 * (1 + b["z"])
+    ref = orc.ec_iso_mono_sed_flux(nu, b["z"], b["d_L"], b["delta_D"], b["mu_s"], b["R_b"], eps_0,
+                                   u_0, b["ne_kind"], b["ne_args"], integrator=integ)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.ExternalCompton.evaluate_sed_flux_iso_mono(
+        nu * u.Hz, b["z"], b["d_L"] * u.cm, b["delta_D"], b["mu_s"], b["R_b"] * u.cm, eps_0,
+        u_0 * u.Unit("erg cm-3"), ne_obj(b["ne_kind"], b["ne_args"]), *q_args(b["ne_args"]),
+        integrator=integrator)
+    assert_parity(got.value, ref, what=f"ec iso {integ}")
+
+
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+def test_ec_ps_behind_jet(integ):
+    b = cases.blob_ec()
+    nu = np.logspace(15, 29, 60)
+    ref = orc.ec_ps_behind_jet_sed_flux(nu, b["z"], b["d_L"], b["delta_D"], b["mu_s"], b["R_b"],
+                                        cases.EPS_LINE, 0.024 * 2e46, 1e19, b["ne_kind"],
+                                        b["ne_args"], integrator=integ)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.ExternalCompton.evaluate_sed_flux_ps_behind_jet(
+        nu * u.Hz, b["z"], b["d_L"] * u.cm, b["delta_D"], b["mu_s"], b["R_b"] * u.cm,
+        cases.EPS_LINE, 0.024 * 2e46 * u.Unit("erg s-1"), 1e19 * u.cm,
+        ne_obj(b["ne_kind"], b["ne_args"]), *q_args(b["ne_args"]), integrator=integrator)
+    assert_parity(got.value, ref, what=f"ec ps {integ}")
+
+
+def test_ec_blr_on_axis_mu_s_1():
+    """mu_s == 1: cos psi == mu*, 1 - cos psi == 0 at mu* == 1 (division by zero in the
+    reference, masked to 0): SURVEY.md 8.2 items 7 and 10."""
+    c = cases.case_c2(n_nu=30, r=1e18)
+    c["mu_s"] = 1.0
+    ref = cases.ORACLE_EC["blr"](c)
+    got = ab.ExternalCompton.evaluate_sed_flux_blr(
+        *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_line"], c["epsilon_line"],
+        c["R_line"] * u.cm, c["r"] * u.cm, *ne_tail(c), gamma=c["gamma"], mu=c["mu"], phi=c["phi"])
+    assert_parity(got.value, ref, what="ec blr mu_s=1")
+
+
+def test_ec_ragged_small_grids():
+    """odd, small grid sizes (partial warps / slices)"""
+    c = cases.case_c2(n_nu=7, r=3e17, n_gamma=53, n_mu=17, n_phi=9)
+    for integ, integrator in (("trapz", np.trapezoid), ("trapz_loglog", ab.trapz_loglog)):
+        ref = cases.ORACLE_EC["blr"](c, integ)
+        got = ab.ExternalCompton.evaluate_sed_flux_blr(
+            *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_line"], c["epsilon_line"],
+            c["R_line"] * u.cm, c["r"] * u.cm, *ne_tail(c), integrator=integrator,
+            gamma=c["gamma"], mu=c["mu"], phi=c["phi"])
+        assert_parity(got.value, ref, what=f"ec blr ragged {integ}")
+
+
+# ---------------------------------------------------------------------------------------------
+# K4 opacities  (BASELINE config 3)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("r", [1.1e16, 1.1e17, 1.1e18])
+def test_tau_blr(r):
+    t = cases.case_tau(n_nu=30)
+    ref = orc.tau_blr(t["nu"], t["z"], 1.0, 2e46, 0.024, cases.EPS_LINE, 1.1e17, r)
+    got = ab.Absorption.evaluate_tau_blr(t["nu"] * u.Hz, t["z"], 1.0, 2e46 * u.Unit("erg s-1"),
+                                         0.024, cases.EPS_LINE, 1.1e17 * u.cm, r * u.cm)
+    assert isinstance(got, np.ndarray)
+    assert_parity(got, ref, what=f"tau blr r={r:g}")
+
+
+def test_tau_blr_nudge():
+    """a path point that coincides with R_line is nudged (targets_absorption.py:335-338)"""
+    t = cases.case_tau(n_nu=12)
+    r = 1e16
+    R_line = float(np.logspace(0, 5, 50)[10] * r)
+    ref = orc.tau_blr(t["nu"], t["z"], 1.0, 2e46, 0.024, cases.EPS_LINE, R_line, r)
+    got = ab.Absorption.evaluate_tau_blr(t["nu"] * u.Hz, t["z"], 1.0, 2e46 * u.Unit("erg s-1"),
+                                         0.024, cases.EPS_LINE, R_line * u.cm, r * u.cm)
+    assert_parity(got, ref, what="tau blr nudge")
+
+
+@pytest.mark.parametrize("r", [1.1e16, 1.1e18, 1.1e19])
+def test_tau_dt(r):
+    t = cases.case_tau(n_nu=200)
+    ref = orc.tau_dt(t["nu"], t["z"], 1.0, 2e46, 0.1, cases.EPS_DT, cases.R_DT, r)
+    got = ab.Absorption.evaluate_tau_dt(t["nu"] * u.Hz, t["z"], 1.0, 2e46 * u.Unit("erg s-1"), 0.1,
+                                        cases.EPS_DT, cases.R_DT * u.cm, r * u.cm)
+    assert_parity(got, ref, what=f"tau dt r={r:g}")
+
+
+@pytest.mark.parametrize("r", [1.1e16, 1.1e17])
+def test_tau_ss_disk(r):
+    t = cases.case_tau(n_nu=30)
+    ref = orc.tau_ss_disk(t["nu"], t["z"], 1.0, cases.M_BH, 2e46, 1 / 12, 6 * cases.R_G,
+                          200 * cases.R_G, r)
+    got = ab.Absorption.evaluate_tau_ss_disk(
+        t["nu"] * u.Hz, t["z"], 1.0, cases.M_BH * u.g, 2e46 * u.Unit("erg s-1"), 1 / 12,
+        6 * cases.R_G * u.cm, 200 * cases.R_G * u.cm, r * u.cm)
+    assert_parity(got, ref, what=f"tau disk r={r:g}")
