@@ -20,7 +20,7 @@ TAU_SS_DISK, TAU_BLR, TAU_DT = 0, 1, 2
 
 EXPORTS = [
     "agnpy_b200_version", "agnpy_b200_last_error", "agnpy_b200_launch_count",
-    "agnpy_b200_fp64_peak",
+    "agnpy_b200_fp64_peak", "agnpy_b200_kernel_timing", "agnpy_b200_kernel_timing_read",
     "agnpy_b200_synch_sed", "agnpy_b200_synch_sed_host",
     "agnpy_b200_ssc_sed", "agnpy_b200_ssc_sed_host",
     "agnpy_b200_ec_sed", "agnpy_b200_ec_sed_host",
@@ -76,6 +76,8 @@ def lib():
     tau = [ip, ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
     L.agnpy_b200_tau.argtypes = tau + [vp]
     L.agnpy_b200_tau_host.argtypes = tau
+    L.agnpy_b200_kernel_timing.argtypes = [C.c_int]
+    L.agnpy_b200_kernel_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     for name in EXPORTS[3:]:
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -90,6 +92,17 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().agnpy_b200_launch_count())
+
+
+def kernel_timing(enable):
+    check(lib().agnpy_b200_kernel_timing(int(bool(enable))), "kernel_timing")
+
+
+def kernel_timing_read():
+    """(total ms, launches) of the dominant kernels timed since kernel_timing(True)"""
+    ms, n = C.c_double(0.0), C.c_longlong(0)
+    check(lib().agnpy_b200_kernel_timing_read(C.byref(ms), C.byref(n)), "kernel_timing_read")
+    return ms.value, n.value
 
 
 def fp64_peak(ms=200.0, stream=None):

@@ -1,0 +1,171 @@
+"""Batched, multi-GPU entry point for fit / MCMC callers (new API).
+
+The reference's fit wrappers (agnpy/fit/sherpa_wrapper.py:51-325, gammapy_wrapper.py:161-357)
+evaluate one parameter vector per call.  Here a batch of parameter vectors ("models") is
+evaluated in one launch sequence on shared integration grids; with torch.distributed
+initialised the batch is sharded over the ranks (one process per GPU) and the per-rank SED
+blocks are joined with ONE NCCL all-gather (every model is independent: no other exchange).
+
+    plan = SedBatch("ec_blr", nu_hz, "BrokenPowerLaw", gamma=..., mu=..., phi=...)
+    sed = plan(models)            # models: numpy structured array of _lib.MODEL_DTYPE, host
+                                  # returns numpy [n_models, n_nu]  (erg cm-2 s-1, or tau)
+
+Grids live on the device for the life of the plan; per call the model table is copied
+host->device from pinned memory and the result device->host into pinned memory.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+_NE_KINDS = {"PowerLaw": _lib.NE_POWERLAW, "BrokenPowerLaw": _lib.NE_BROKEN_POWERLAW,
+             "LogParabola": _lib.NE_LOG_PARABOLA, "ExpCutoffPowerLaw": _lib.NE_EXP_CUTOFF_POWERLAW,
+             "ExpCutoffBrokenPowerLaw": _lib.NE_EXP_CUTOFF_BROKEN_POWERLAW}
+_EC = {"ec_iso_mono": _lib.EC_ISO_MONO, "ec_ps_behind_jet": _lib.EC_PS_BEHIND_JET,
+       "ec_ss_disk": _lib.EC_SS_DISK, "ec_blr": _lib.EC_BLR, "ec_dt": _lib.EC_DT}
+_TAU = {"tau_ss_disk": _lib.TAU_SS_DISK, "tau_blr": _lib.TAU_BLR, "tau_dt": _lib.TAU_DT}
+PROCESSES = ("synch", "ssc") + tuple(_EC) + tuple(_TAU)
+
+
+# ---- sharding arithmetic (pure; covered by the gloo tests on CPU) ---------------------------
+def partition(n_models, world_size):
+    """models per rank (padded so every rank holds the same count) -> (per_rank, padded_total)"""
+    per_rank = -(-n_models // world_size)
+    return per_rank, per_rank * world_size
+
+
+def local_slice(n_models, world_size, rank):
+    """[lo, hi) of the real models owned by `rank`, and the padded per-rank count"""
+    per_rank, _ = partition(n_models, world_size)
+    lo = min(rank * per_rank, n_models)
+    hi = min(lo + per_rank, n_models)
+    return lo, hi, per_rank
+
+
+def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu"):
+    """Run `local_compute(models[lo:hi]) -> tensor [hi-lo, n_nu]` on this rank's shard and
+    all-gather the blocks.  Without an initialised process group this is a plain call."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return local_compute(models)
+    rank = dist.get_rank(group)
+    n = len(models)
+    lo, hi, per_rank = local_slice(n, world, rank)
+    block = torch.zeros(per_rank, n_nu, dtype=torch.float64, device=device)
+    if hi > lo:
+        block[: hi - lo] = local_compute(models[lo:hi])
+    out = torch.empty(world * per_rank, n_nu, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    return out[:n]
+
+
+# ---- the GPU plan -----------------------------------------------------------------------------
+class SedBatch:
+    """One radiative process on fixed grids, evaluated for batches of models on one GPU
+    (or sharded over the ranks of `group`)."""
+
+    def __init__(self, process, nu, ne_kind="BrokenPowerLaw", *, gamma=None, mu=None, phi=None,
+                 nu_seed=None, mu_size=100, l_size=50, ssa=False, integrator="trapz",
+                 device=None, group=None):
+        import torch
+        from . import grids
+        if process not in PROCESSES:
+            raise ValueError(f"process must be one of {PROCESSES}")
+        if not torch.cuda.is_available():
+            raise _lib.AgnpyB200Error("SedBatch needs a CUDA device: agnpy_b200 has no CPU fallback")
+        lib()
+        self.torch = torch
+        self.process = process
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.group = group
+        self.ne_kind = _NE_KINDS[ne_kind] if isinstance(ne_kind, str) else int(ne_kind)
+        self.integ = grids.integrator_code(integrator)
+        self.ssa = int(bool(ssa))
+        self.mu_size = int(mu_size)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        self.nu = dev(np.ravel(nu))
+        self.n_nu = self.nu.numel()
+        if gamma is None:
+            gamma = grids.gamma_e_to_integrate
+        self.gamma = dev(grids.as_grid(gamma, "gamma"))
+        self.mu = dev(grids.mu_to_integrate if mu is None else grids.as_grid(mu, "mu"))
+        self.phi = dev(grids.phi_to_integrate if phi is None else grids.as_grid(phi, "phi"))
+        self.nu_seed = dev(grids.nu_to_integrate if nu_seed is None else nu_seed)
+        self.l_unit = dev(np.logspace(0, 5, int(l_size)))
+        self._pinned_in = self._pinned_out = self._d_models = self._d_out = None
+
+    # -- buffers sized for the largest batch seen so far
+    def _buffers(self, n):
+        torch = self.torch
+        if self._d_models is None or self._d_models.shape[0] < n:
+            self._pinned_in = torch.empty(n, _lib.MODEL_DOUBLES, dtype=torch.float64).pin_memory()
+            self._pinned_out = torch.empty(n, self.n_nu, dtype=torch.float64).pin_memory()
+            self._d_models = torch.empty(n, _lib.MODEL_DOUBLES, dtype=torch.float64, device=self.device)
+            self._d_out = torch.empty(n, self.n_nu, dtype=torch.float64, device=self.device)
+        return self._pinned_in[:n], self._pinned_out[:n], self._d_models[:n], self._d_out[:n]
+
+    def launch(self, d_models, d_out, stream=None):
+        """enqueue the kernels for device-resident models [n, 22] -> d_out [n, n_nu]"""
+        torch = self.torch
+        n = d_models.shape[0]
+        st = (torch.cuda.current_stream(self.device) if stream is None else stream).cuda_stream
+        L, p = lib(), self.process
+        if p == "synch":
+            rc = L.agnpy_b200_synch_sed(n, d_models.data_ptr(), self.ne_kind, self.nu.data_ptr(),
+                                        self.n_nu, self.gamma.data_ptr(), self.gamma.numel(), None,
+                                        None, self.ssa, self.integ, d_out.data_ptr(), None, st)
+        elif p == "ssc":
+            rc = L.agnpy_b200_ssc_sed(n, d_models.data_ptr(), self.ne_kind, self.nu.data_ptr(),
+                                      self.n_nu, self.nu_seed.data_ptr(), self.nu_seed.numel(),
+                                      self.gamma.data_ptr(), self.gamma.numel(), None, None,
+                                      self.ssa, self.integ, d_out.data_ptr(), st)
+        elif p in _EC:
+            v = _EC[p]
+            mu_ptr = self.mu.data_ptr() if v in (_lib.EC_ISO_MONO, _lib.EC_BLR) else None
+            n_mu = self.mu_size if v == _lib.EC_SS_DISK else self.mu.numel()
+            rc = L.agnpy_b200_ec_sed(v, n, d_models.data_ptr(), self.ne_kind, self.nu.data_ptr(),
+                                     self.n_nu, self.gamma.data_ptr(), self.gamma.numel(), mu_ptr,
+                                     n_mu, self.phi.data_ptr(), self.phi.numel(), None, self.integ,
+                                     d_out.data_ptr(), st)
+        else:
+            v = _TAU[p]
+            mu_ptr = self.mu.data_ptr() if v == _lib.TAU_BLR else None
+            n_a = self.mu_size if v == _lib.TAU_SS_DISK else self.mu.numel()
+            rc = L.agnpy_b200_tau(v, n, d_models.data_ptr(), self.nu.data_ptr(), self.n_nu, mu_ptr,
+                                  n_a, self.phi.data_ptr(), self.phi.numel(),
+                                  self.l_unit.data_ptr(), self.l_unit.numel(), d_out.data_ptr(), st)
+        check(rc, f"agnpy_b200 {p}")
+        return d_out
+
+    def _local(self, models):
+        """host models -> device result for this rank's shard (H2D from pinned memory)"""
+        n = len(models)
+        pin_in, _, d_models, d_out = self._buffers(n)
+        pin_in.numpy()[...] = np.ascontiguousarray(models).view(np.float64).reshape(n, -1)
+        d_models.copy_(pin_in, non_blocking=True)
+        return self.launch(d_models, d_out)
+
+    def evaluate_device(self, models):
+        """as __call__ but returns the (gathered) device tensor without the D2H copy"""
+        return sharded_evaluate(self._local, models, self.n_nu, self.group, self.device)
+
+    def __call__(self, models):
+        if models.dtype != _lib.MODEL_DTYPE:
+            raise TypeError("models must be a numpy array of agnpy_b200._lib.MODEL_DTYPE")
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            out = self.evaluate_device(models)
+            n = out.shape[0]
+            if self._pinned_out is None or self._pinned_out.shape[0] < n:
+                self._pinned_out = torch.empty(n, self.n_nu, dtype=torch.float64).pin_memory()
+            host = self._pinned_out[:n]
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy().copy()
+
+
+def evaluate_sed_batch(process, nu, models, ne_kind="BrokenPowerLaw", **kwargs):
+    """one-shot convenience: build a plan and evaluate `models` (see SedBatch)"""
+    return SedBatch(process, nu, ne_kind, **kwargs)(models)

@@ -79,10 +79,12 @@ int agnpy_b200_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
     for (int m0 = 0; m0 < n_models; m0 += chunk) {
         int nm = std::min(chunk, n_models - m0);
         launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, ssa_table, 0, tab, stream);
-        if (int rc = launch_synch(models + m0, nm, nu, n_nu, tab, n_gamma, ssa, integ, 0,
-                                  sed + (size_t)m0 * n_nu,
-                                  tau_ssa ? tau_ssa + (size_t)m0 * n_nu : nullptr, nullptr, stream))
-            return rc;
+        timing_begin(stream);
+        int rc_s = launch_synch(models + m0, nm, nu, n_nu, tab, n_gamma, ssa, integ, 0,
+                                sed + (size_t)m0 * n_nu,
+                                tau_ssa ? tau_ssa + (size_t)m0 * n_nu : nullptr, nullptr, stream);
+        timing_end(stream);
+        if (rc_s) return rc_s;
     }
     return check_last("synch_sed");
 }
@@ -115,9 +117,11 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         if (int rc = launch_synch(models + m0, nm, nu_seed, n_seed, tab, n_gamma, ssa, integ, 1, U,
                                   nullptr, es, stream))
             return rc;
-        if (int rc = launch_ssc(models + m0, nm, nu, n_nu, tab, n_gamma, U, es, n_seed, integ,
-                                sed + (size_t)m0 * n_nu, stream))
-            return rc;
+        timing_begin(stream);
+        int rc_ssc = launch_ssc(models + m0, nm, nu, n_nu, tab, n_gamma, U, es, n_seed, integ,
+                                sed + (size_t)m0 * n_nu, stream);
+        timing_end(stream);
+        if (rc_ssc) return rc_ssc;
     }
     return check_last("ssc_sed");
 }

@@ -207,5 +207,8 @@ void note_launch(int n = 1);
 void* workspace(size_t bytes, cudaStream_t stream);
 int fail(int code, const char* what);
 int check_last(const char* what);
+// CUDA-event bracket around the dominant kernel of a call (no-ops unless enabled)
+void timing_begin(cudaStream_t stream);
+void timing_end(cudaStream_t stream);
 
 }  // namespace agb

@@ -366,6 +366,7 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     size_t smem = (size_t)n_gamma * sizeof(double) * (integ == AGNPY_INTEG_TRAPZ ? 4 : 7);
     if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for the EC kernel");
     dim3 grid(p.S, n_nu, n_models);
+    timing_begin(stream);
     if (integ == AGNPY_INTEG_LOGLOG)
         launch_main<AGNPY_INTEG_LOGLOG, 1>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
     else if (p.J == 4)
@@ -374,6 +375,7 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         launch_main<AGNPY_INTEG_TRAPZ, 2>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
     else
         launch_main<AGNPY_INTEG_TRAPZ, 1>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
+    timing_end(stream);
     note_launch();
     {
         dim3 g2((n_nu + 127) / 128, n_models);

@@ -58,6 +58,33 @@ void* workspace(size_t bytes, cudaStream_t stream) {
     return s.ptr;
 }
 
+// ---- optional CUDA-event timing of the dominant kernel of a call (bench.py roofline) ---------
+static bool g_timing = false;
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+static double g_timed_ms = 0.0;
+static long long g_timed_n = 0;
+static bool g_pending = false;
+
+static void timing_collect() {
+    if (!g_pending) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_t1) == cudaSuccess && cudaEventElapsedTime(&ms, g_t0, g_t1) == cudaSuccess) {
+        g_timed_ms += ms;
+        g_timed_n += 1;
+    }
+    g_pending = false;
+}
+void timing_begin(cudaStream_t stream) {
+    if (!g_timing) return;
+    timing_collect();
+    cudaEventRecord(g_t0, stream);
+}
+void timing_end(cudaStream_t stream) {
+    if (!g_timing) return;
+    cudaEventRecord(g_t1, stream);
+    g_pending = true;
+}
+
 // ---- FP64 peak probe: 8 independent DFMA chains per thread, all SMs full -------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
@@ -80,6 +107,26 @@ extern "C" {
 const char* agnpy_b200_version(void) { return "agnpy_b200 0.1.0 (sm_100a)"; }
 const char* agnpy_b200_last_error(void) { return agb::g_err.c_str(); }
 long long agnpy_b200_launch_count(void) { return agb::g_launches.load(); }
+
+int agnpy_b200_kernel_timing(int enable) {
+    using namespace agb;
+    if (enable && !g_t0) {
+        if (cudaEventCreate(&g_t0) != cudaSuccess || cudaEventCreate(&g_t1) != cudaSuccess)
+            return check_last("kernel_timing");
+    }
+    if (!enable) timing_collect();
+    g_timing = enable != 0;
+    if (enable) { g_timed_ms = 0.0; g_timed_n = 0; g_pending = false; }
+    return AGNPY_OK;
+}
+
+int agnpy_b200_kernel_timing_read(double* total_ms, long long* n_launches) {
+    using namespace agb;
+    timing_collect();
+    *total_ms = g_timed_ms;
+    *n_launches = g_timed_n;
+    return AGNPY_OK;
+}
 
 int agnpy_b200_fp64_peak(double ms, double* flops_per_s, void* stream_) {
     using namespace agb;

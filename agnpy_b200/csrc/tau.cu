@@ -210,7 +210,9 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
     }
     {
         dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
+        timing_begin(stream);
         tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, part);
+        timing_end(stream);
         note_launch();
     }
     {

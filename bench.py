@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- SED evaluations/s of the emission-integral hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) "C2"): external Compton on the Lyman-alpha
+spherical-shell BLR, default grids 200 nu x 200 gamma x 100 mu x 50 phi = 2e8 integrand points
+per SED.  A *step* evaluates a batch of MODELS_PER_GPU independent parameter vectors per GPU
+(different r, delta_D, electron spectrum...) through the batched entry point; at N>1 the batch
+is sharded over ranks (weak scaling) and the SED blocks are joined by one NCCL all-gather
+inside the timed step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # CUDA arm
+  python bench.py --impl reference [...]                       # CPU arm: oracle port, all cores
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` goes through the public host-buffer API (pinned H2D of the model table, D2H of
+the SEDs, wall clock); `roofline` is for the dominant kernel ec_main_kernel; `cpu_baseline` is
+the oracle (reference arithmetic, 1 core) timed on this box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODELS_PER_GPU = 256
+N_NU, N_GAMMA, N_MU, N_PHI = 200, 200, 100, 50
+FLOPS_PER_POINT = 16          # nominal FP64 ops per compton_kernel point (np.trapz)
+EXEC_FLOPS_PER_POINT = 6      # executed: DMUL + DADD + DFMA + DFMA (FMA = 2)
+METRIC = "SED evals/sec (EC-BLR)"
+UNIT = "SED/s"
+WORKLOAD = ("configs[1]: ExternalCompton on SphericalShellBLR (Lyalpha), 200 nu x 200 gamma x "
+            "100 mu x 50 phi, np.trapz")
+
+
+# ---------------------------------------------------------------------------------------------
+def synthetic_models(n, seed=20261019):
+    """parameter vectors in the fit ranges of SURVEY.md 8(d) C5 (agnpy/fit/core.py:92-157) on the
+    C2 physics: returns a numpy array of agnpy_b200._lib.MODEL_DTYPE"""
+    from agnpy_b200 import _core, _lib
+    from tests import cases
+    rng = np.random.default_rng(seed)
+    models = _lib.make_models(n)
+    for i in range(n):
+        delta = rng.uniform(10, 40)
+        beta = np.sqrt(1 - 1 / delta**2)
+        mu_s = (1 - 1 / (delta * delta)) / beta
+        ne = [10 ** rng.uniform(-9, -7), rng.uniform(1.5, 2.5), rng.uniform(3, 4),
+              10 ** rng.uniform(3.5, 5), 20.0, 5e7, 0.0, 0.0]
+        R_b = 2.99792458e10 * 86400.0 * delta / (1 + cases.Z_EC)
+        _core.model_row(models, i, z=cases.Z_EC, d_L=cases.D_L_EC, delta_D=delta, mu_s=mu_s,
+                        B=10 ** rng.uniform(-1.5, 0), R_b=R_b, ne=ne,
+                        tgt=[cases.L_DISK, cases.XI_LINE, cases.EPS_LINE, cases.R_LINE,
+                             10 ** rng.uniform(17, 19)])
+    return models
+
+
+def grids():
+    return dict(nu=np.logspace(15, 30, N_NU), gamma=np.logspace(1, 9, N_GAMMA),
+                mu=np.linspace(-1, 1, N_MU), phi=np.linspace(0, 2 * np.pi, N_PHI))
+
+
+def oracle_sed(model, g, nu=None):
+    from oracle import agnpy_oracle as orc
+    nu = g["nu"] if nu is None else nu
+    return orc.ec_blr_sed_flux(nu, model["z"], model["d_L"], model["delta_D"], model["mu_s"],
+                               model["R_b"], model["tgt"][0], model["tgt"][1], model["tgt"][2],
+                               model["tgt"][3], model["tgt"][4], "BrokenPowerLaw",
+                               tuple(model["ne"][:6]), gamma=g["gamma"], mu=g["mu"], phi=g["phi"])
+
+
+def executed_point_fraction(models, g):
+    """fraction of the full (gamma, mu, phi, nu) grid the kernel actually visits: points with
+    gamma >= gamma_min(nu, mu, phi) inside the non-zero range of n_e (the rest is exactly 0 in
+    the reference too).  Reported next to the algorithmic figure, never folded into it."""
+    from oracle import agnpy_oracle as orc
+    tot = vis = 0
+    for m in models[: min(len(models), 16)]:
+        eps_s = orc.nu_to_epsilon_prime(g["nu"], m["z"])
+        R_line, r = m["tgt"][3], m["tgt"][4]
+        with np.errstate(all="ignore"):
+            ms = orc.mu_star_shell(g["mu"], R_line, r)
+            gmin = orc.gamma_min_compton(eps_s[None, None, :], m["tgt"][2], m["mu_s"],
+                                         ms[:, None, None], g["phi"][None, :, None])
+        gam = g["gamma"]
+        live = (gam / m["delta_D"] >= m["ne"][4]) & (gam / m["delta_D"] <= m["ne"][5])
+        klo, khi = np.argmax(live), len(gam) - 1 - np.argmax(live[::-1])
+        k0 = np.searchsorted(gam, np.nan_to_num(gmin, nan=np.inf), side="left")
+        vis += np.clip(khi + 1 - np.maximum(k0, klo), 0, None).sum()
+        tot += gmin.size * len(gam)
+    return float(vis) / float(tot)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.split(",") for r in Path(self.file.name).read_text().splitlines() if r.strip()]
+        os.unlink(self.file.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from agnpy_b200 import _lib
+    from agnpy_b200.batch import SedBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (agnpy_b200 has no CPU fallback; "
+                         "use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    g = grids()
+    total = MODELS_PER_GPU * world
+    models = synthetic_models(total)
+    plan = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"], phi=g["phi"],
+                    device=dev)
+    lo, hi = rank * MODELS_PER_GPU, (rank + 1) * MODELS_PER_GPU
+    local = models[lo:hi]
+    d_models = torch.from_numpy(np.ascontiguousarray(local).view(np.float64)
+                                .reshape(len(local), -1).copy()).to(dev)
+    d_out = torch.empty(len(local), N_NU, dtype=torch.float64, device=dev)
+    gathered = torch.empty(total, N_NU, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    def step():
+        plan.launch(d_models, d_out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, CUDA events per step, L2 flushed between steps --------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in evs:
+        flush.fill_(1.0)
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = total / (ms_per_step * 1e-3)
+
+    # ---- e2e: public host-buffer API (pinned H2D of models, kernels, gather, D2H), wall clock ---
+    plan_e2e = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"],
+                        phi=g["phi"], device=dev, group=None if world == 1 else dist.group.WORLD)
+    for _ in range(3):
+        res = plan_e2e(models)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = plan_e2e(models)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total * args.steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 only from here: parity spot check, roofline, single-call latency, CPU baseline --
+    from tests import cases
+    chk = oracle_sed(models[0], g, nu=g["nu"][::8])
+    dev_rel, zeros_ok = cases.max_rel_dev(res[0][::8], chk)
+
+    peak = _lib.fp64_peak(300.0)
+    _lib.kernel_timing(True)
+    for _ in range(max(3, min(args.steps, 10))):
+        plan.launch(d_models, d_out)
+    torch.cuda.synchronize()
+    kms, kn = _lib.kernel_timing_read()
+    _lib.kernel_timing(False)
+    k_ms = kms / max(kn, 1)
+    pts_per_launch = len(local) * N_NU * N_GAMMA * N_MU * N_PHI
+    achieved = pts_per_launch * FLOPS_PER_POINT / (k_ms * 1e-3) / 1e12
+    frac_pts = executed_point_fraction(local, g)
+    executed = pts_per_launch * frac_pts * EXEC_FLOPS_PER_POINT / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tfile = ROOT / "profiles" / "ec_main_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # single-call drop-in latency (the literal reference call with Quantities)
+    import agnpy_b200 as ab
+    from agnpy_b200 import spectra, u
+    c = cases.case_c2()
+    ne = spectra.BrokenPowerLaw(*c["ne_args"])
+    qa = (c["ne_args"][0] * u.Unit("cm-3"),) + tuple(c["ne_args"][1:])
+
+    def one():
+        return ab.ExternalCompton.evaluate_sed_flux_blr(
+            c["nu"] * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["mu_s"], c["R_b"] * u.cm,
+            c["L_disk"] * u.Unit("erg s-1"), c["xi_line"], c["epsilon_line"], c["R_line"] * u.cm,
+            c["r"] * u.cm, ne, *qa, gamma=c["gamma"], mu=c["mu"], phi=c["phi"])
+    for _ in range(5):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        one()
+    single_us = (time.perf_counter() - t0) / 50 * 1e6
+
+    # CPU baseline: the oracle (reference arithmetic), 1 core, bounded sample
+    t0 = time.perf_counter()
+    n_cpu = 0
+    while True:
+        _oracle_chunked(models[n_cpu], g)
+        n_cpu += 1
+        if time.perf_counter() - t0 > 12 or n_cpu >= 3:
+            break
+    cpu_dt = time.perf_counter() - t0
+    cpu_value = n_cpu / cpu_dt
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "models_per_gpu_per_step": MODELS_PER_GPU,
+                   "points_per_sed": N_NU * N_GAMMA * N_MU * N_PHI,
+                   "l2": "flushed between timed steps (256 MiB write); inputs are KB-sized, "
+                         "the path is FP64-pipe bound",
+                   "collective": "none" if world == 1 else "one NCCL all_gather_into_tensor of "
+                                 f"{MODELS_PER_GPU}x{N_NU} f64 per rank inside the step",
+                   "parity_vs_oracle_max_rel_dev": dev_rel, "parity_zeros_exact": zeros_ok},
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(total * 176),
+                "d2h_bytes_per_step": int(total * N_NU * 8),
+                "api": "agnpy_b200.batch.SedBatch.__call__ (host numpy in/out, pinned staging)",
+                "single_call_us": single_us,
+                "single_call_api": "ExternalCompton.evaluate_sed_flux_blr (Quantity in/out, "
+                                   "agnpy_b200_ec_sed_host)"},
+        "integrand_gpts_per_s": total * N_NU * N_GAMMA * N_MU * N_PHI / (ms_per_step * 1e-3) / 1e9,
+        "roofline": {
+            "bound": "fp64", "kernel": "ec_main_kernel<trapz,J=4>", "achieved": achieved,
+            "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
+            "traffic": traffic,
+            "peak_source": "live DFMA-chain microbenchmark agnpy_b200_fp64_peak on this GPU "
+                           "(MEASURED_PEAKS.json has no FP64 entry)",
+            "kernel_ms": k_ms, "kernel_launches_timed": int(kn),
+            "algorithmic_flops_per_point": FLOPS_PER_POINT,
+            "executed": {"tflops": executed, "frac": executed / (peak / 1e12),
+                         "fp64_flops_per_visited_point": EXEC_FLOPS_PER_POINT,
+                         "visited_point_fraction": frac_pts},
+            "note": "frac > 1 is expected: the nominal 16 flop/point charges two divisions and the "
+                    "(gamma,nu)/(mu,phi)-only subexpressions per point; the kernel hoists them "
+                    "(4 FP64 instr/point) and skips points the reference masks to exactly 0. "
+                    "'executed' counts only instructions actually issued."},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{n_cpu} SED(s) of the same workload (oracle = reference numpy "
+                                   "arithmetic, nu-chunked by 25), 1 thread",
+                         "host_cpus": os.cpu_count()},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _oracle_chunked(model, g, chunk=25):
+    return np.concatenate([oracle_sed(model, g, nu=g["nu"][i:i + chunk])
+                           for i in range(0, N_NU, chunk)])
+
+
+# ---------------------------------------------------------------------------------------------
+def _ref_worker(job):
+    model_bytes, lo, hi = job
+    from agnpy_b200 import _lib
+    model = np.frombuffer(model_bytes, dtype=_lib.MODEL_DTYPE)[0]
+    g = grids()
+    return oracle_sed(model, g, nu=g["nu"][lo:hi])
+
+
+def run_reference(args):
+    """CPU arm: the reference cannot be installed here (astropy/matplotlib absent, no network),
+    so this times the oracle port (the reference's numpy arithmetic) on all host cores: one
+    step = one SED of the same workload, its 200 frequencies split over a process pool."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    chunk = 4
+    models = synthetic_models(max(args.steps + args.warmup, 1))
+    jobs_for = lambda m: [(m.tobytes(), lo, min(lo + chunk, N_NU)) for lo in range(0, N_NU, chunk)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for i in range(args.warmup):
+            pool.map(_ref_worker, jobs_for(models[i:i + 1]))
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pool.map(_ref_worker, jobs_for(models[args.warmup + i:args.warmup + i + 1]))
+        dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "1 SED per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} step(s) x 1 SED, nu split in chunks of {chunk} "
+                                   f"over {cores} processes",
+                         "host_cpus": os.cpu_count(),
+                         "why_port": "agnpy needs astropy+matplotlib, not installable offline; the "
+                                     "oracle restates its numpy arithmetic (oracle/agnpy_oracle.py)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,10 @@ const char* agnpy_b200_version(void);
 const char* agnpy_b200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench "gpu_launches") */
 long long agnpy_b200_launch_count(void);
+/* CUDA-event timing of the dominant kernel of each call (ec_main / ssc / tau_main / synch),
+ * on the launching stream; for the roofline line of bench.py.  Not thread safe. */
+int agnpy_b200_kernel_timing(int enable);
+int agnpy_b200_kernel_timing_read(double* total_ms, long long* n_launches);
 /* measured FP64 peak of the current device [FLOP/s]: a dependent-free DFMA-chain
  * microbenchmark run for `ms` milliseconds (roofline denominator) */
 int agnpy_b200_fp64_peak(double ms, double* flops_per_s, void* stream);
