@@ -1,0 +1,161 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the
+header declares, fails loudly without a GPU, and the Quantity / electron-distribution /
+integrator marshalling behaves like the reference boundary."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import agnpy_b200 as ab
+from agnpy_b200 import _lib, grids, spectra, u
+from agnpy_b200.units import Quantity, strip, wrap
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "agnpy_b200.h").read_text()
+    return sorted(set(re.findall(r"\b(agnpy_b200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert _lib.LIB_PATH.exists(), "build the library first: python agnpy_b200/build.py"
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/agnpy_b200.h but not exported"
+    assert set(_lib.EXPORTS) == set(syms)
+    assert b"sm_100a" in _lib.lib().agnpy_b200_version()
+
+
+def test_model_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.Model) == 22 * 8 == _lib.MODEL_DTYPE.itemsize
+    assert _lib.MODEL_DTYPE.fields["ne"][1] == 48 and _lib.MODEL_DTYPE.fields["tgt"][1] == 112
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ne = spectra.PowerLaw(1e-8, 2.0, 10, 1e5)
+    with pytest.raises(_lib.AgnpyB200Error, match="no CUDA device"):
+        ab.Synchrotron.evaluate_sed_flux(np.logspace(9, 15, 4) * u.Hz, 0.1, 1e27 * u.cm, 10,
+                                         1 * u.G, 1e16 * u.cm, ne, *ne.parameters)
+    with pytest.raises(_lib.AgnpyB200Error):
+        ab.Absorption.evaluate_tau_dt(np.logspace(24, 27, 4) * u.Hz, 0.1, 1.0,
+                                      1e45 * u.Unit("erg s-1"), 0.1, 1e-6, 1e18 * u.cm, 1e17 * u.cm)
+    from agnpy_b200.batch import SedBatch
+    with pytest.raises(_lib.AgnpyB200Error):
+        SedBatch("ec_blr", np.logspace(15, 30, 8))
+
+
+def test_product_never_imports_the_oracle():
+    for path in list((ROOT / "agnpy_b200").rglob("*.py")) + list((ROOT / "agnpy_b200").rglob("*.cu*")):
+        assert "oracle" not in path.read_text(), f"{path} mentions the oracle"
+
+
+def test_units_strip_and_wrap():
+    assert strip(1 * u.Mpc, "cm") == pytest.approx(3.0856775814913673e24)
+    assert strip(3 * u.G, "G") == 3.0
+    assert strip(2e45 * u.Unit("erg s-1"), "erg s-1") == 2e45
+    assert strip(1e7 * u.Unit("erg s-1"), "W") == pytest.approx(1.0)
+    assert strip(1e-8 * u.Unit("cm-3"), "cm-3") == 1e-8
+    assert strip(5.0, "cm") == 5.0                      # plain numbers are taken as CGS
+    np.testing.assert_array_equal(strip(np.arange(3.0) * u.Hz, "Hz"), np.arange(3.0))
+    with pytest.raises(TypeError):
+        strip(1 * u.cm, "Hz")
+    with pytest.raises(TypeError):
+        strip("ten", "cm")
+    q = wrap(np.ones(4), "erg cm-2 s-1")
+    assert q.unit == u.Unit("erg cm-2 s-1") and q.shape == (4,)
+    assert isinstance(np.float64(2.0) * u.g, Quantity)
+    assert (1 * u.G).to_value("cm(-1/2) g(1/2) s-1") == 1.0   # conversion.py:11-12
+
+
+def test_spectra_describe_follows_reference_parameter_order():
+    ne = spectra.BrokenPowerLaw(1e-8 * u.Unit("cm-3"), 2.0, 3.5, 1e4, 20, 5e7)
+    kind, par = spectra.describe(ne, ne.parameters)
+    assert kind == _lib.NE_BROKEN_POWERLAW
+    np.testing.assert_array_equal(par[:6], [1e-8, 2.0, 3.5, 1e4, 20, 5e7])
+    ne = spectra.ExpCutoffBrokenPowerLaw(1e-9, 1.8, 2.9, 2e5, 1e4, 10, 1e6)
+    kind, par = spectra.describe(ne, ne.parameters)
+    assert kind == _lib.NE_EXP_CUTOFF_BROKEN_POWERLAW and par[3] == 2e5 and par[4] == 1e4
+
+    class PowerLaw:  # an object of the reference's own class is recognised by name
+        tag = "PowerLaw"
+    assert spectra.describe(PowerLaw(), [1e-7, 2.1, 10, 1e5])[0] == _lib.NE_POWERLAW
+    with pytest.raises(ValueError):
+        spectra.describe(PowerLaw(), [1e-7, 2.1, 10])
+    with pytest.raises(TypeError):
+        spectra.describe(object(), [1.0])
+
+
+def test_snap_boundaries_like_reference():
+    g = np.logspace(1, 5, 50)
+    g[0], g[-1] = np.nextafter(10.0, 0), np.nextafter(1e5, 2e5)
+    s = spectra.snap_boundaries(g, 10.0, 1e5)
+    assert s[0] == 10.0 and s[-1] == 1e5 and g[0] != 10.0      # works on a copy
+    far = spectra.snap_boundaries(np.logspace(0.9, 5.1, 50), 10.0, 1e5)
+    assert far[0] != 10.0 and far[-1] != 1e5                   # only within 1e-10
+
+
+def test_interpolated_distribution_table():
+    gam = np.logspace(1, 6, 60)
+    n = 1e-3 * gam**-2.2
+    n[:3] = 0
+    ne = spectra.InterpolatedDistribution(gam, n * u.Unit("cm-3"), norm=2.0)
+    assert ne.gamma_min == gam[3] and ne.gamma_max == gam[-1]
+    kind, par = spectra.describe(ne, ne.parameters)
+    assert kind == _lib.NE_TABLE and par[0] == 2.0
+    grid = np.logspace(0.5, 6.5, 100)
+    table, ssa = spectra.tables(ne, ne.parameters, grid, True)
+    inside = (grid >= ne.gamma_min) & (grid <= ne.gamma_max)
+    assert np.all(table[~inside] == 0)
+    np.testing.assert_allclose(table[inside], 2.0 * 1e-3 * grid[inside] ** -2.2, rtol=1e-6)
+    np.testing.assert_allclose(ssa[inside], -4.2 * table[inside] / grid[inside], rtol=1e-4)
+
+
+def test_integrator_dispatch():
+    assert grids.integrator_code(np.trapezoid) == _lib.INTEG_TRAPZ
+    if hasattr(np, "trapz"):
+        assert grids.integrator_code(np.trapz) == _lib.INTEG_TRAPZ
+    assert grids.integrator_code(ab.trapz_loglog) == _lib.INTEG_LOGLOG
+
+    def trapz_loglog(y, x, axis=0):  # the reference's function is recognised by name
+        return None
+    assert grids.integrator_code(trapz_loglog) == _lib.INTEG_LOGLOG
+    with pytest.raises(ValueError):
+        grids.integrator_code(np.sum)
+    with pytest.raises(NotImplementedError):
+        ab.trapz_loglog(np.ones(3), np.arange(3))
+
+
+def test_grid_validation():
+    with pytest.raises(ValueError):
+        grids.as_grid([1.0], "gamma")
+    with pytest.raises(ValueError):
+        grids.as_grid([3.0, 2.0, 1.0], "gamma")
+    np.testing.assert_array_equal(grids.gamma_e_to_integrate, np.logspace(1, 9, 200))
+    np.testing.assert_array_equal(grids.nu_to_integrate, np.logspace(5, 30, 200))
+
+
+def test_targets_and_blob_containers():
+    from agnpy_b200 import targets
+    blr = targets.SphericalShellBLR(2e46 * u.Unit("erg s-1"), 0.024, "Lyalpha", 1e17 * u.cm)
+    assert blr.epsilon_line == pytest.approx(1.9958625603e-05, rel=1e-9)
+    dt = targets.RingDustTorus(2e46 * u.Unit("erg s-1"), 0.1, 1e3 * u.K)
+    assert strip(dt.R_dt, "cm") == pytest.approx(1.5652e19, rel=1e-4)
+    with pytest.raises(NameError):
+        targets.SphericalShellBLR(1e45, 0.1, "Unobtainium", 1e17)
+    disk = targets.SSDisk(1.2e9 * 1.988409870698051e33 * u.g, 2e46 * u.Unit("erg s-1"), 1 / 12, 6, 200,
+                          R_g_units=True)
+    assert disk.R_in_tilde == 6 and strip(disk.R_out, "cm") / strip(disk.R_g, "cm") == pytest.approx(200)
+    ne = spectra.PowerLaw(1e-8, 2.0, 10, 1e5)
+    blob = targets.Blob(1e16 * u.cm, 1.0, 2e28 * u.cm, 40, 40, 1 * u.G, ne)
+    assert blob.mu_s == pytest.approx((1 - 1 / 1600) / np.sqrt(1 - 1 / 1600))
+    assert blob.gamma_e[0] == pytest.approx(10) and blob.gamma_e_external_frame.size == 200
+    with pytest.raises(ValueError):
+        ab.Absorption(blr)  # r is mandatory, targets_absorption.py:68-73

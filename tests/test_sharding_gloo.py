@@ -1,0 +1,76 @@
+"""The N>1 path on CPU: batch sharding + one all-gather over a world_size-2 gloo group.
+The GPU compute is replaced by the oracle (tests may use it), so what is exercised is the
+host logic of agnpy_b200.batch: partition, padding, gather order, trimming."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from agnpy_b200 import _core, _lib
+from agnpy_b200.batch import local_slice, partition, sharded_evaluate
+
+
+def test_partition_arithmetic():
+    assert partition(10, 4) == (3, 12)
+    assert partition(8, 8) == (1, 8)
+    assert partition(1, 8) == (1, 8)
+    covered = []
+    for r in range(4):
+        lo, hi, per = local_slice(10, 4, r)
+        assert per == 3
+        covered += list(range(lo, hi))
+    assert covered == list(range(10))
+    assert local_slice(1, 8, 5) == (1, 1, 1)          # empty shard
+
+
+def _models(n):
+    models = _lib.make_models(n)
+    for i in range(n):
+        _core.model_row(models, i, z=0.05 * i, d_L=1e27, delta_D=10 + i, B=0.5, R_b=1e16,
+                        ne=[1e-8, 2.0 + 0.05 * i, 10.0, 1e5, 0, 0, 0, 0])
+    return models
+
+
+def _cpu_compute(nu):
+    from oracle import agnpy_oracle as orc
+
+    def f(models):
+        out = [orc.synch_sed_flux(nu, m["z"], m["d_L"], m["delta_D"], m["B"], m["R_b"], "PowerLaw",
+                                  tuple(m["ne"][:4]), gamma=np.logspace(1, 5, 60)) for m in models]
+        return torch.from_numpy(np.array(out).reshape(len(models), nu.size))
+    return f
+
+
+def _worker(rank, world, port, n_models, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nu = np.logspace(9, 18, 12)
+    out = sharded_evaluate(_cpu_compute(nu), _models(n_models), nu.size, device="cpu")
+    q.put((rank, out.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_models", [5, 4, 1])
+def test_sharded_evaluate_world2_gloo(n_models):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_models, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nu = np.logspace(9, 18, 12)
+    full = _cpu_compute(nu)(_models(n_models)).numpy()
+    for r in range(2):
+        assert results[r].shape == (n_models, nu.size)
+        np.testing.assert_array_equal(results[r], full)   # every rank holds the whole batch
