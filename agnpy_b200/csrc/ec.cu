@@ -18,6 +18,8 @@
 // the reference's own operation order (kernels.py:36-40) and turned into a start index of
 // the gamma loop by a binary search of the (ascending) gamma grid.
 #include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -62,14 +64,12 @@ __device__ __forceinline__ double disk_epsilon(double L_disk, double M_BH, doubl
 //                        ang[m][1][j] = 1 - cos psi_j
 //                        ang[m][2][j] = b_j = 1/(eps_j (1 - cos psi_j))
 //                        ang[m][3][j] = W_j        np.trapz weights x geometric factor
+//                        ang[m][4][j] = c_j = 2 eps_j (1 - cos psi_j)   (mask threshold on G)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ec_pairs_kernel(
-    int variant, const agnpy_model_t* __restrict__ models, const double* __restrict__ mu,
-    int n_mu, const double* __restrict__ phi, int n_phi, int n_pairs, double* __restrict__ ang) {
-    int m = blockIdx.y;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void ec_pairs_role(
+    int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_mu,
+    const double* __restrict__ phi, int n_phi, int n_pairs, double* __restrict__ row, int j) {
     if (j >= n_pairs) return;
-    const agnpy_model_t& M = models[m];
     const double* t = M.tgt;
     double eps, cpsi, W;
     if (variant == AGNPY_EC_PS_BEHIND_JET) {  // external_compton.py:226: mu = 1, phi = 0
@@ -115,155 +115,271 @@ __global__ void __launch_bounds__(128) ec_pairs_kernel(
         }
     }
     double omc = 1.0 - cpsi;
-    double* row = ang + (size_t)m * 4 * n_pairs;
     row[j] = eps;
     row[n_pairs + j] = omc;
     row[2 * n_pairs + j] = 1.0 / (eps * omc);
     row[3 * n_pairs + j] = W;
+    row[4 * n_pairs + j] = 2.0 * (eps * omc);
 }
 
 // ---------------------------------------------------------------------------------------------
-// main kernel.  grid = (S slices, n_nu, n_models), block = T threads, J pairs per thread.
-// shared (trapz):  gamma_k | wf_k = w_k N_e/gamma^2 | A_k | G_k
-// shared (loglog): gamma_k | f_k = N_e/gamma^2 | ln f_k | A_k | G_k | 1/(ln g_k - ln g_k+1) | ln(g_k+1/g_k)
-// part[m][i][slice] = sum over the slice's pairs of W_j * integral_gamma
+// gamma tables of one model (nu independent), K5 fused in: N_e = V_b n_e(snap(gamma/delta_D))
+// (external_compton.py:125-126; the integration grid itself stays unsnapped)
+//         gt[m][0][k] = gamma_k
+//         gt[m][1][k] = trapz: w_k N_e/gamma^2   loglog: f_k = N_e/gamma^2
+//         gt[m][2][k] = ln f_k                    gt[m][3][k] = 1/(ln g_k - ln g_{k+1})
+//         gt[m][4][k] = ln(g_{k+1}/g_k)           hull[m] = {klo, khi}: non-zero range of n_e
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ec_gamma_role(
+    const agnpy_model_t& M, int ne_kind, const double* __restrict__ gamma, int n_gamma,
+    const double* __restrict__ ne_table, int integ, double* __restrict__ row,
+    int* __restrict__ hull2, int* s_hull) {
+    if (threadIdx.x == 0) { s_hull[0] = n_gamma; s_hull[1] = -1; }
+    __syncthreads();
+    double gmin, gmax;
+    if (ne_kind == AGNPY_NE_TABLE) { gmin = M.ne[1]; gmax = M.ne[2]; }
+    else ne_bounds(ne_kind, M.ne, gmin, gmax);
+    const double V_b = 4.0 / 3.0 * kPi * (M.R_b * M.R_b * M.R_b);
+    const double d = M.delta_D, g0 = gamma[0] / d, gN = gamma[n_gamma - 1] / d;
+    for (int k = threadIdx.x; k < n_gamma; k += blockDim.x) {
+        double g = gamma[k];
+        double ne = (ne_kind == AGNPY_NE_TABLE)
+                        ? ne_table[k]
+                        : ne_eval(ne_kind, M.ne, snapped(g / d, k, n_gamma, g0, gN, gmin, gmax));
+        double f = (V_b * ne) / (g * g);
+        row[k] = g;
+        if (integ == AGNPY_INTEG_TRAPZ) {
+            row[n_gamma + k] = f * trapz_weight(gamma, k, n_gamma);
+        } else {
+            row[n_gamma + k] = f;
+            row[2 * n_gamma + k] = clipped_log(f);
+            if (k < n_gamma - 1) {
+                double gu = gamma[k + 1];
+                row[3 * n_gamma + k] = 1.0 / (clipped_log(g) - clipped_log(gu));
+                row[4 * n_gamma + k] = clipped_log(gu / g);
+            }
+        }
+        if (f != 0.0) { atomicMin(&s_hull[0], k); atomicMax(&s_hull[1], k); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { hull2[0] = s_hull[0]; hull2[1] = s_hull[1]; }
+}
+
+// per-(gamma, nu) table of one model:  nt[m][i][k] = {A, G},
+//   y = 1 - eps_s/gamma,  A = y + 1/y,  G = eps_s/(gamma^2 y)  (+inf where gamma <= eps_s)
+__device__ __forceinline__ void ec_nu_role(const agnpy_model_t& M, const double* __restrict__ nu,
+                                           const double* __restrict__ gamma, int n_gamma,
+                                           double2* __restrict__ nt_row, int i, int k) {
+    if (k >= n_gamma) return;
+    // EC uses nu_to_epsilon_prime(nu, z) without the Doppler factor (external_compton.py:123)
+    const double eps_s = nu_to_eps(nu[i], M.z, 1.0);
+    const double g = gamma[k];
+    const double y = 1.0 - eps_s / g;
+    double2 v;
+    v.x = y + 1.0 / y;
+    v.y = (y > 0.0) ? eps_s / ((g * g) * y) : INFINITY;
+    nt_row[(size_t)i * n_gamma + k] = v;
+}
+
+// One launch builds all three tables; the block role follows from blockIdx.x:
+//   [0, 1)                     gamma tables + hull
+//   [1, 1 + nB)                pair table, 128 pairs per block
+//   [1 + nB, 1 + nB + nC*n_nu) {A, G} table, 128 gammas of one frequency per block
+__global__ void __launch_bounds__(128) ec_tables_kernel(
+    int variant, const agnpy_model_t* __restrict__ models, int ne_kind,
+    const double* __restrict__ nu, int n_nu, const double* __restrict__ gamma, int n_gamma,
+    const double* __restrict__ mu, int n_mu, const double* __restrict__ phi, int n_phi,
+    const double* __restrict__ ne_table, int integ, int n_pairs, double* __restrict__ gt,
+    int* __restrict__ hull, double* __restrict__ ang, double2* __restrict__ nt) {
+    __shared__ int s_hull[2];
+    const int m = blockIdx.y;
+    const agnpy_model_t& M = models[m];
+    const int nB = (n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;
+    int bx = blockIdx.x;
+    if (bx == 0) {
+        ec_gamma_role(M, ne_kind, gamma, n_gamma, ne_table, integ, gt + (size_t)m * 5 * n_gamma,
+                      hull + 2 * m, s_hull);
+    } else if (bx < 1 + nB) {
+        ec_pairs_role(variant, M, mu, n_mu, phi, n_phi, n_pairs, ang + (size_t)m * 5 * n_pairs,
+                      (bx - 1) * 128 + threadIdx.x);
+    } else {
+        bx -= 1 + nB;
+        ec_nu_role(M, nu, gamma, n_gamma, nt + (size_t)m * n_nu * n_gamma, bx / nC,
+                   (bx % nC) * 128 + threadIdx.x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel.  grid = (Sg <= S slice groups, n_nu, n_models), block = T threads, J (mu,phi)
+// pairs per thread.  The block copies the per-gamma values of its (nu, model) -- produced by
+// the two table kernels above -- into shared memory once, then every warp walks its slices of
+// pairs independently (no barrier after the copy): per slice it locates the first unmasked
+// gamma index of each pair, runs the gamma loop from shared-memory broadcasts, reduces with
+// shuffles and stores its own partial:
+// part[m][i][slice][warp] = sum over that warp's pairs of W_j * integral_gamma.
+//
+// Kinematic mask.  In exact arithmetic gamma >= gamma_min(eps_s, eps, psi)  <=>  t = G b <= 2, so
+// the first unmasked index is the first k with G_k <= c, c = 2 eps (1 - cos psi): a binary search
+// of the descending G table, no division or square root per (nu, pair).  The J searches of a
+// thread run interleaved and branch-free (fixed trip count) so their shared-memory latencies
+// overlap.  numpy decides the mask on fl(gamma_min); the two can only disagree when G_k is
+// within rounding of c, so whenever a neighbour of the found index lies within a 1e-6 relative
+// band of c (or y_k < 1e-8, where G_k itself is ill-conditioned) the index is recomputed from
+// gamma_min in the reference's own operation order (kernels.py:36-40).  The band is ~1e9 ulp
+// wide and is hit by ~1e-5 of the lookups.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ int first_unmasked_exact(const double* __restrict__ gm, int n_gamma,
+                                                 double eps, double eps_s, double omc) {
+    double root = sqrt(1.0 + 2.0 / (eps * eps_s * omc));
+    double gmin = eps_s / 2.0 * (1.0 + root);
+    int lo = 0, hi = n_gamma;  // first k with gamma_k >= gmin (NaN -> n_gamma)
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (gm[mid] >= gmin) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 template <int INTEG, int J>
 __global__ void __launch_bounds__(256) ec_main_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
-    const double* __restrict__ tab, int n_gamma, const double* __restrict__ ang, int n_pairs,
+    const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma, int search_iters,
+    const double2* __restrict__ nt, const double* __restrict__ ang, int n_pairs, int S,
     double* __restrict__ part) {
     extern __shared__ double sh[];
-    __shared__ double red[32];
-    __shared__ int s_klo, s_khi;
-    const int slice = blockIdx.x, i = blockIdx.y, m = blockIdx.z, S = gridDim.x;
-    const int T = blockDim.x, tid = threadIdx.x;
-    const agnpy_model_t& M = models[m];
-    const double* gs = tab + (size_t)m * 3 * n_gamma;
-    const double* Ne = gs + n_gamma;
-    // EC uses nu_to_epsilon_prime(nu, z) without the Doppler factor (external_compton.py:123)
-    const double eps_s = nu_to_eps(nu[i], M.z, 1.0);
-    double* s_gm = sh;
-    double* s_f = s_gm + n_gamma;
+    const int i = blockIdx.y, m = blockIdx.z;
+    const int T = blockDim.x, tid = threadIdx.x, W_per_block = T >> 5;
+    const double* g_gm = gt + (size_t)m * 5 * n_gamma;
+    const double* g_f = g_gm + n_gamma;
+    const double2* AG = nt + ((size_t)m * n_nu + i) * n_gamma;
+    double* s_f = sh;
     double* s_A = s_f + n_gamma;
     double* s_G = s_A + n_gamma;
-    double* s_lf = s_G + n_gamma;    // loglog only
+    double* s_gm = s_G + n_gamma;    // loglog only
+    double* s_lf = s_gm + n_gamma;   // loglog only
     double* s_idl = s_lf + n_gamma;  // loglog only
     double* s_lr = s_idl + n_gamma;  // loglog only
-    if (tid == 0) { s_klo = n_gamma; s_khi = -1; }
-    __syncthreads();
     for (int k = tid; k < n_gamma; k += T) {
-        double g = gs[k];
-        double f = Ne[k] / (g * g);
-        double y = 1.0 - eps_s / g;
-        s_gm[k] = g;
-        s_A[k] = y + 1.0 / y;
-        s_G[k] = eps_s / ((g * g) * y);
-        if (INTEG == AGNPY_INTEG_TRAPZ) {
-            s_f[k] = f * trapz_weight(gs, k, n_gamma);
-        } else {
-            s_f[k] = f;
-            s_lf[k] = clipped_log(f);
-            if (k < n_gamma - 1) {
-                double gu = gs[k + 1];
-                s_idl[k] = 1.0 / (clipped_log(g) - clipped_log(gu));
-                s_lr[k] = clipped_log(gu / g);
-            }
+        double2 ag = AG[k];
+        s_f[k] = g_f[k];
+        s_A[k] = ag.x;
+        s_G[k] = ag.y;
+        if (INTEG == AGNPY_INTEG_LOGLOG) {
+            s_gm[k] = g_gm[k];
+            s_lf[k] = g_gm[2 * n_gamma + k];
+            s_idl[k] = g_gm[3 * n_gamma + k];
+            s_lr[k] = g_gm[4 * n_gamma + k];
         }
-        if (f != 0.0) { atomicMin(&s_klo, k); atomicMax(&s_khi, k); }
     }
+    const int klo = hull[2 * m], khi = hull[2 * m + 1];  // non-zero range of n_e
     __syncthreads();
-    const int klo = s_klo, khi = s_khi;  // hull of the non-zero electron distribution
 
-    const double* a_eps = ang + (size_t)m * 4 * n_pairs;
+    const double* a_eps = ang + (size_t)m * 5 * n_pairs;
     const double* a_omc = a_eps + n_pairs;
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
-    double b[J], W[J], acc[J];
-    int k0[J];
-    int kmin = INT_MAX, kmax = 0;
-#pragma unroll
-    for (int jj = 0; jj < J; ++jj) {
-        int j = slice * (T * J) + jj * T + tid;
-        bool valid = j < n_pairs;
-        acc[jj] = 0.0;
-        b[jj] = 0.0;
-        W[jj] = 0.0;
-        k0[jj] = n_gamma;
-        if (valid) {
-            b[jj] = a_b[j];
-            W[jj] = a_W[j];
-            // kernels.py:36-40 in the reference's operation order
-            double root = sqrt(1.0 + 2.0 / (a_eps[j] * eps_s * a_omc[j]));
-            double gmin = eps_s / 2.0 * (1.0 + root);
-            int lo = 0, hi = n_gamma;  // first k with gamma_k >= gmin (NaN -> n_gamma)
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (s_gm[mid] >= gmin) hi = mid; else lo = mid + 1;
-            }
-            k0[jj] = lo;
-            kmin = min(kmin, lo);
-            kmax = max(kmax, lo);
-        }
-    }
-    double thread_sum = 0.0;
-    if (khi >= 0) {
-        if (INTEG == AGNPY_INTEG_TRAPZ) {
-            kmin = __reduce_min_sync(0xffffffffu, kmin);
-            kmax = __reduce_max_sync(0xffffffffu, kmax);
-            int kbeg = max(kmin, klo);
-            int kmid = min(max(kmax, kbeg), khi + 1);
-            // phase 1: some lanes still below their gamma_min -> predicated accumulate
-            for (int k = kbeg; k < kmid; ++k) {
-                double wf = s_f[k], A = s_A[k], G = s_G[k];
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) {
-                    double t = G * b[jj];
-                    double K = fma(t, t - 2.0, A);
-                    if (k >= k0[jj]) acc[jj] = fma(wf, K, acc[jj]);
-                }
-            }
-            // phase 2: every valid lane is above its gamma_min -> 4 FP64 instructions / point
-            for (int k = kmid; k <= khi; ++k) {
-                double wf = s_f[k], A = s_A[k], G = s_G[k];
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) {
-                    double t = G * b[jj];
-                    double K = fma(t, t - 2.0, A);
-                    acc[jj] = fma(wf, K, acc[jj]);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj) {
-                int ks = max(k0[jj], klo);
-                double y_prev = 0.0, ly_prev = 0.0, a = 0.0;
-                for (int k = ks; k <= khi; ++k) {
-                    double f = s_f[k];
-                    double y = 0.0, ly = 0.0;
-                    if (f != 0.0) {
-                        double t = s_G[k] * b[jj];
-                        double K = fma(t, t - 2.0, s_A[k]);
-                        y = f * K;
-                        ly = clipped_log(y);
-                    }
-                    if (k > ks)
-                        a += loglog_interval_pre(s_gm[k - 1], s_gm[k], s_idl[k - 1], s_lr[k - 1],
-                                                 y_prev, y, ly_prev, ly);
-                    y_prev = y;
-                    ly_prev = ly;
-                }
-                acc[jj] = a;
-            }
-        }
+    const double* a_c = a_W + n_pairs;
+    for (int slice = blockIdx.x; slice < S; slice += gridDim.x) {
+        double b[J], W[J], c[J], acc[J];
+        int lo[J], hi[J];
 #pragma unroll
         for (int jj = 0; jj < J; ++jj) {
             int j = slice * (T * J) + jj * T + tid;
-            if (j < n_pairs) thread_sum = fma(W[jj], acc[jj], thread_sum);
+            bool valid = j < n_pairs;
+            b[jj] = valid ? a_b[j] : 0.0;
+            W[jj] = valid ? a_W[j] : 0.0;
+            c[jj] = valid ? a_c[j] : -1.0;  // c <= 0: never unmasked
+            acc[jj] = 0.0;
+            lo[jj] = 0;
+            hi[jj] = n_gamma;
         }
+        // J interleaved branch-free binary searches: first k with G_k <= c
+        for (int it = 0; it < search_iters; ++it) {
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                int mid = (lo[jj] + hi[jj]) >> 1;
+                bool open = lo[jj] < hi[jj];
+                bool le = s_G[min(mid, n_gamma - 1)] <= c[jj];
+                hi[jj] = (open && le) ? mid : hi[jj];
+                lo[jj] = (open && !le) ? mid + 1 : lo[jj];
+            }
+        }
+        int kmin = INT_MAX, kmax = 0;
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) {
+            int k = lo[jj];
+            const double cj = c[jj], band = 1e-6 * cj;
+            int ka = min(k, n_gamma - 1), kb = max(k - 1, 0);
+            double Ga = s_G[ka], Aa = s_A[ka], Gb = s_G[kb], Ab = s_A[kb];
+            bool doubt = (k < n_gamma && (fabs(Ga - cj) <= band || Aa > 1e8)) ||
+                         (k > 0 && (fabs(Gb - cj) <= band || (Ab > 1e8 && Gb < kFmax)));
+            doubt = (doubt || !(cj < kFmax)) && cj > 0.0;
+            if (doubt) {
+                int j = slice * (T * J) + jj * T + tid;
+                k = first_unmasked_exact(g_gm, n_gamma, a_eps[j], nu_to_eps(nu[i], models[m].z, 1.0),
+                                         a_omc[j]);
+            }
+            lo[jj] = k;
+            if (cj > 0.0) { kmin = min(kmin, k); kmax = max(kmax, k); }
+        }
+        double thread_sum = 0.0;
+        if (khi >= 0) {
+            if (INTEG == AGNPY_INTEG_TRAPZ) {
+                kmin = __reduce_min_sync(0xffffffffu, kmin);
+                kmax = __reduce_max_sync(0xffffffffu, kmax);
+                int kbeg = max(kmin, klo);
+                int kmid = min(max(kmax, kbeg), khi + 1);
+                // phase 1: some lanes still below their gamma_min -> predicated accumulate
+                for (int k = kbeg; k < kmid; ++k) {
+                    double wf = s_f[k], A = s_A[k], G = s_G[k];
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) {
+                        double t = G * b[jj];
+                        double K = fma(t, t - 2.0, A);
+                        if (k >= lo[jj]) acc[jj] = fma(wf, K, acc[jj]);
+                    }
+                }
+                // phase 2: every valid lane is above its gamma_min -> 4 FP64 instructions / point
+                for (int k = kmid; k <= khi; ++k) {
+                    double wf = s_f[k], A = s_A[k], G = s_G[k];
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) {
+                        double t = G * b[jj];
+                        double K = fma(t, t - 2.0, A);
+                        acc[jj] = fma(wf, K, acc[jj]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    int ks = max(lo[jj], klo);
+                    double y_prev = 0.0, ly_prev = 0.0, a = 0.0;
+                    for (int k = ks; k <= khi; ++k) {
+                        double f = s_f[k];
+                        double y = 0.0, ly = 0.0;
+                        if (f != 0.0) {
+                            double t = s_G[k] * b[jj];
+                            double K = fma(t, t - 2.0, s_A[k]);
+                            y = f * K;
+                            ly = clipped_log(y);
+                        }
+                        if (k > ks)
+                            a += loglog_interval_pre(s_gm[k - 1], s_gm[k], s_idl[k - 1], s_lr[k - 1],
+                                                     y_prev, y, ly_prev, ly);
+                        y_prev = y;
+                        ly_prev = ly;
+                    }
+                    acc[jj] = a;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj)
+                if (c[jj] > 0.0) thread_sum = fma(W[jj], acc[jj], thread_sum);
+        }
+        thread_sum = warp_sum(thread_sum);
+        if ((tid & 31) == 0)
+            part[(((size_t)m * n_nu + i) * S + slice) * W_per_block + (tid >> 5)] = thread_sum;
     }
-    thread_sum = block_sum(thread_sum, red);
-    if (tid == 0) part[((size_t)m * n_nu + i) * S + slice] = thread_sum;
 }
 
 // sum the slices in a fixed order and apply the prefactor of each evaluate_sed_flux_*
@@ -321,32 +437,54 @@ static int ec_n_pairs(int variant, int n_mu, int n_phi) {
 
 struct EcPlan {
     int n_pairs, T, J, S;
+    int W() const { return T / 32; }  // partials per slice
 };
 static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
     EcPlan p;
     p.n_pairs = ec_n_pairs(variant, n_mu, n_phi);
-    p.T = p.n_pairs <= 32 ? 32 : p.n_pairs <= 64 ? 64 : p.n_pairs <= 128 ? 128 : 256;
+    p.T = p.n_pairs <= 32 ? 32 : p.n_pairs <= 64 ? 64 : 128;
     p.J = 1;
-    if (integ == AGNPY_INTEG_TRAPZ) p.J = p.n_pairs >= 2048 ? 4 : p.n_pairs >= 512 ? 2 : 1;
+    // measured on B200 (scripts/tune_ec.py): 128 threads x 8 pairs is the fastest tile at the
+    // default 5000 pairs; smaller pair counts keep more, smaller tiles
+    if (integ == AGNPY_INTEG_TRAPZ) p.J = p.n_pairs >= 2048 ? 8 : p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
+    if (const char* e = getenv("AGNPY_B200_EC_PLAN")) {  // development knob: "T,J"
+        int t = 0, j = 0;
+        if (sscanf(e, "%d,%d", &t, &j) == 2 && t >= 32 && t <= 256 && t % 32 == 0 &&
+            (j == 1 || j == 2 || j == 4 || j == 8) && (integ == AGNPY_INTEG_TRAPZ || j == 1)) {
+            p.T = t;
+            p.J = j;
+        }
+    }
     p.S = (p.n_pairs + p.T * p.J - 1) / (p.T * p.J);
     return p;
 }
 
+// doubles of scratch per model
+static size_t ec_words(const EcPlan& p, int n_nu, int n_gamma) {
+    return 5 * (size_t)n_gamma + 2      // gamma tables + hull (2 ints in one double slot, padded)
+           + 5 * (size_t)p.n_pairs      // pair table
+           + 2 * (size_t)n_nu * n_gamma // {A,G}
+           + (size_t)n_nu * p.S * p.W();
+}
+
 size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi) {
-    EcPlan p = ec_plan(variant, n_mu, n_phi, AGNPY_INTEG_LOGLOG);  // J=1 -> largest S
-    size_t per = 3 * (size_t)n_gamma + 4 * (size_t)p.n_pairs + (size_t)n_nu * p.S;
-    return per * sizeof(double) * (size_t)n_models;
+    EcPlan a = ec_plan(variant, n_mu, n_phi, AGNPY_INTEG_LOGLOG);  // J=1 -> largest S
+    EcPlan b = ec_plan(variant, n_mu, n_phi, AGNPY_INTEG_TRAPZ);
+    size_t per = ec_words(a, n_nu, n_gamma);
+    size_t per_b = ec_words(b, n_nu, n_gamma);
+    return (per > per_b ? per : per_b) * sizeof(double) * (size_t)n_models + 256;
 }
 
 template <int INTEG, int J>
 static void launch_main(dim3 grid, int T, size_t smem, cudaStream_t stream,
-                        const agnpy_model_t* models, const double* nu, int n_nu, const double* tab,
-                        int n_gamma, const double* ang, int n_pairs, double* part) {
+                        const agnpy_model_t* models, const double* nu, int n_nu, const double* gt,
+                        const int* hull, int n_gamma, int iters, const double2* nt,
+                        const double* ang, int n_pairs, int S, double* part) {
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(ec_main_kernel<INTEG, J>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
-    ec_main_kernel<INTEG, J><<<grid, T, smem, stream>>>(models, nu, n_nu, tab, n_gamma, ang,
-                                                        n_pairs, part);
+    ec_main_kernel<INTEG, J><<<grid, T, smem, stream>>>(models, nu, n_nu, gt, hull, n_gamma, iters,
+                                                        nt, ang, n_pairs, S, part);
 }
 
 int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, const double* nu,
@@ -354,32 +492,54 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
            const double* phi, int n_phi, const double* ne_table, int integ, double* sed,
            double* ws, cudaStream_t stream) {
     EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
-    double* tab = ws;
-    double* ang = tab + (size_t)n_models * 3 * n_gamma;
-    double* part = ang + (size_t)n_models * 4 * p.n_pairs;
-    launch_prep_gamma(models, n_models, ne_kind, gamma, n_gamma, ne_table, nullptr, 1, tab, stream);
+    const size_t M = (size_t)n_models;
+    // carve: {A,G} table first (16-byte aligned: ws comes from cudaMalloc), then the rest
+    double2* nt = (double2*)ws;
+    double* gt = (double*)(nt + M * n_nu * n_gamma);
+    double* ang = gt + M * 5 * n_gamma;
+    double* part = ang + M * 5 * p.n_pairs;
+    int* hull = (int*)(part + M * n_nu * p.S * p.W());
     {
-        dim3 grid((p.n_pairs + 127) / 128, n_models);
-        ec_pairs_kernel<<<grid, 128, 0, stream>>>(variant, models, mu, n_mu, phi, n_phi, p.n_pairs, ang);
+        int nB = (p.n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;
+        dim3 grid(1 + nB + nC * n_nu, n_models);
+        ec_tables_kernel<<<grid, 128, 0, stream>>>(variant, models, ne_kind, nu, n_nu, gamma, n_gamma,
+                                                   mu, n_mu, phi, n_phi, ne_table, integ, p.n_pairs,
+                                                   gt, hull, ang, nt);
         note_launch();
     }
-    size_t smem = (size_t)n_gamma * sizeof(double) * (integ == AGNPY_INTEG_TRAPZ ? 4 : 7);
+    size_t smem = (size_t)n_gamma * sizeof(double) * (integ == AGNPY_INTEG_TRAPZ ? 3 : 7);
     if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for the EC kernel");
-    dim3 grid(p.S, n_nu, n_models);
+    // slice groups per (nu, model): a block walks all its slices once the grid fills the GPU
+    // many times over (amortises the table copy), else one block per slice (latency)
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int Sg = p.S;
+    while (Sg > 1 && (long long)n_nu * n_models * ((Sg + 1) / 2) >= 32LL * sms) Sg = (Sg + 1) / 2;
+    if (const char* e = getenv("AGNPY_B200_EC_SG")) {  // development knob
+        int v = atoi(e);
+        if (v >= 1) Sg = v < p.S ? v : p.S;
+    }
+    int iters = 1;
+    while ((1 << iters) < n_gamma + 1) ++iters;
+    dim3 grid(Sg, n_nu, n_models);
     timing_begin(stream);
-    if (integ == AGNPY_INTEG_LOGLOG)
-        launch_main<AGNPY_INTEG_LOGLOG, 1>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
-    else if (p.J == 4)
-        launch_main<AGNPY_INTEG_TRAPZ, 4>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
-    else if (p.J == 2)
-        launch_main<AGNPY_INTEG_TRAPZ, 2>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
-    else
-        launch_main<AGNPY_INTEG_TRAPZ, 1>(grid, p.T, smem, stream, models, nu, n_nu, tab, n_gamma, ang, p.n_pairs, part);
+#define EC_LAUNCH(I, JJ) launch_main<I, JJ>(grid, p.T, smem, stream, models, nu, n_nu, gt, hull, \
+                                            n_gamma, iters, nt, ang, p.n_pairs, p.S, part)
+    if (integ == AGNPY_INTEG_LOGLOG) EC_LAUNCH(AGNPY_INTEG_LOGLOG, 1);
+    else if (p.J == 8) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 8);
+    else if (p.J == 4) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 4);
+    else if (p.J == 2) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 2);
+    else EC_LAUNCH(AGNPY_INTEG_TRAPZ, 1);
+#undef EC_LAUNCH
     timing_end(stream);
     note_launch();
     {
         dim3 g2((n_nu + 127) / 128, n_models);
-        ec_finish_kernel<<<g2, 128, 0, stream>>>(variant, models, nu, n_nu, part, p.S, sed);
+        ec_finish_kernel<<<g2, 128, 0, stream>>>(variant, models, nu, n_nu, part, p.S * p.W(), sed);
         note_launch();
     }
     return check_last("ec_sed");
