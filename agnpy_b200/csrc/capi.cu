@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/agnpy_b200.h: argument checks, workspace
 // carving, batching of the model axis, and the host-pointer flavours (H2D, run, D2H, sync).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -184,75 +185,144 @@ int agnpy_b200_tau(int variant, int n_models, const agnpy_model_t* models, const
     return AGNPY_OK;
 }
 
-// ==========================================================================================
-// host-pointer flavours: one device arena per call holds inputs and outputs; the kernel
-// scratch comes from the stream workspace as in the device flavours.
-// ==========================================================================================
-#define H2D(dst, src, n, T)                                                                     \
-    if ((src) && cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, st) \
-                     != cudaSuccess)                                                            \
-        return check_last("H2D copy");
-#define D2H(dst, src, n, T)                                                                     \
-    if ((dst) && cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToHost, st) \
-                     != cudaSuccess)                                                            \
-        return check_last("D2H copy");
+}  // extern "C"
 
-static void* io_arena(size_t bytes) {
-    // separate cache from the kernel workspace: keyed by a sentinel stream value
-    static thread_local void* ptr[64] = {};
-    static thread_local size_t size[64] = {};
+// ==========================================================================================
+// host-pointer flavours.  All inputs are packed into one pinned staging block and go to the
+// device with ONE cudaMemcpyAsync; outputs come back with one more (small calls are latency
+// bound: a dozen pageable copies would cost more than the kernels).  Blocks above 8 MiB skip
+// the staging copy and are transferred straight from / to the caller's memory.
+// ==========================================================================================
+namespace agb {
+
+static void* cached_alloc(size_t bytes, bool pinned) {
+    static thread_local void* ptr[2][64] = {};
+    static thread_local size_t size[2][64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
-    if (size[dev] >= bytes) return ptr[dev];
-    if (ptr[dev]) {
+    const int w = pinned ? 1 : 0;
+    if (size[w][dev] >= bytes) return ptr[w][dev];
+    if (ptr[w][dev]) {
         cudaDeviceSynchronize();
-        cudaFree(ptr[dev]);
-        ptr[dev] = nullptr;
-        size[dev] = 0;
+        if (pinned) cudaFreeHost(ptr[w][dev]); else cudaFree(ptr[w][dev]);
+        ptr[w][dev] = nullptr;
+        size[w][dev] = 0;
     }
     size_t want = bytes + bytes / 4 + (1u << 16);
-    if (cudaMalloc(&ptr[dev], want) != cudaSuccess) {
+    cudaError_t e = pinned ? cudaHostAlloc(&ptr[w][dev], want, cudaHostAllocDefault)
+                           : cudaMalloc(&ptr[w][dev], want);
+    if (e != cudaSuccess) {
         cudaGetLastError();
-        ptr[dev] = nullptr;
+        ptr[w][dev] = nullptr;
         return nullptr;
     }
-    size[dev] = want;
-    return ptr[dev];
+    size[w][dev] = want;
+    return ptr[w][dev];
 }
+
+struct HostIO {
+    static constexpr size_t kStageLimit = (size_t)8 << 20;
+    struct Buf { const void* h_in; void* h_out; size_t bytes, off; };
+    std::vector<Buf> bufs;
+    size_t in_end = 0, total = 0;
+    char* dbase = nullptr;
+    char* pbase = nullptr;
+    bool staged = false;
+    cudaStream_t st = 0;
+
+    int in(const void* h, size_t bytes) {  // register an input (h may be NULL -> no buffer)
+        bufs.push_back({h, nullptr, h ? bytes : 0, 0});
+        return (int)bufs.size() - 1;
+    }
+    int out(void* h, size_t bytes) {
+        bufs.push_back({nullptr, h, h ? bytes : 0, 0});
+        return (int)bufs.size() - 1;
+    }
+    // inputs must all be registered before outputs
+    int commit() {
+        size_t off = 0;
+        for (auto& b : bufs) {
+            if (b.h_out && in_end == 0) in_end = off;
+            b.off = off;
+            off += pad(b.bytes);
+        }
+        if (in_end == 0) in_end = off;
+        total = off + 256;
+        st = host_stream();
+        dbase = (char*)cached_alloc(total, false);
+        if (!dbase) return fail(AGNPY_ERR_NOMEM, "host call: device memory");
+        staged = total <= kStageLimit;
+        if (staged) {
+            pbase = (char*)cached_alloc(total, true);
+            if (!pbase) staged = false;
+        }
+        return AGNPY_OK;
+    }
+    template <class T>
+    T* dev(int idx) const {
+        const Buf& b = bufs[idx];
+        return b.bytes ? (T*)(dbase + b.off) : nullptr;
+    }
+    int upload() {
+        if (staged) {
+            for (auto& b : bufs)
+                if (b.h_in && b.bytes) memcpy(pbase + b.off, b.h_in, b.bytes);
+            if (in_end && cudaMemcpyAsync(dbase, pbase, in_end, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                return check_last("H2D copy");
+        } else {
+            for (auto& b : bufs)
+                if (b.h_in && b.bytes &&
+                    cudaMemcpyAsync(dbase + b.off, b.h_in, b.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                    return check_last("H2D copy");
+        }
+        return AGNPY_OK;
+    }
+    int download() {
+        size_t out_bytes = total - 256 - in_end;
+        if (staged) {
+            if (out_bytes && cudaMemcpyAsync(pbase + in_end, dbase + in_end, out_bytes,
+                                             cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                return check_last("D2H copy");
+            if (cudaStreamSynchronize(st) != cudaSuccess) return check_last("host call");
+            for (auto& b : bufs)
+                if (b.h_out && b.bytes) memcpy(b.h_out, pbase + b.off, b.bytes);
+        } else {
+            for (auto& b : bufs)
+                if (b.h_out && b.bytes &&
+                    cudaMemcpyAsync(b.h_out, dbase + b.off, b.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                    return check_last("D2H copy");
+            if (cudaStreamSynchronize(st) != cudaSuccess) return check_last("host call");
+        }
+        return AGNPY_OK;
+    }
+};
+
+}  // namespace agb
+
+extern "C" {
 
 int agnpy_b200_synch_sed_host(int n_models, const agnpy_model_t* models, int ne_kind,
                               const double* nu, int n_nu, const double* gamma, int n_gamma,
                               const double* ne_table, const double* ssa_table, int ssa,
                               int integ, double* sed, double* tau_ssa) {
     if (int rc = need_device()) return rc;
-    if (n_models < 1 || n_nu < 1 || n_gamma < 2) return fail(AGNPY_ERR_ARG, "synch_sed_host: bad sizes");
-    cudaStream_t st = host_stream();
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || !models || !nu || !gamma || !sed)
+        return fail(AGNPY_ERR_ARG, "synch_sed_host: bad sizes or null pointer");
     size_t out_n = (size_t)n_models * n_nu;
-    size_t bytes = pad(sizeof(agnpy_model_t) * n_models) + pad(8 * (size_t)n_nu) +
-                   3 * pad(8 * (size_t)n_gamma) + 2 * pad(8 * out_n) + 4096;
-    void* base = io_arena(bytes);
-    if (!base) return fail(AGNPY_ERR_NOMEM, "synch_sed_host: device memory");
-    Arena a(base);
-    agnpy_model_t* d_models = a.take<agnpy_model_t>(n_models);
-    double* d_nu = a.take<double>(n_nu);
-    double* d_gamma = a.take<double>(n_gamma);
-    double* d_net = ne_table ? a.take<double>(n_gamma) : nullptr;
-    double* d_sat = ssa_table ? a.take<double>(n_gamma) : nullptr;
-    double* d_sed = a.take<double>(out_n);
-    double* d_tau = tau_ssa ? a.take<double>(out_n) : nullptr;
-    H2D(d_models, models, n_models, agnpy_model_t);
-    H2D(d_nu, nu, n_nu, double);
-    H2D(d_gamma, gamma, n_gamma, double);
-    H2D(d_net, ne_table, n_gamma, double);
-    H2D(d_sat, ssa_table, n_gamma, double);
-    if (int rc = agnpy_b200_synch_sed(n_models, d_models, ne_kind, d_nu, n_nu, d_gamma, n_gamma,
-                                      d_net, d_sat, ssa, integ, d_sed, d_tau, st))
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int i_sa = io.in(ssa_table, 8 * (size_t)n_gamma);
+    int o_sed = io.out(sed, 8 * out_n), o_tau = io.out(tau_ssa, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_synch_sed(n_models, io.dev<agnpy_model_t>(i_m), ne_kind, io.dev<double>(i_nu),
+                                      n_nu, io.dev<double>(i_g), n_gamma, io.dev<double>(i_ne),
+                                      io.dev<double>(i_sa), ssa, integ, io.dev<double>(o_sed),
+                                      io.dev<double>(o_tau), io.st))
         return rc;
-    D2H(sed, d_sed, out_n, double);
-    D2H(tau_ssa, d_tau, out_n, double);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return check_last("synch_sed_host");
-    return AGNPY_OK;
+    return io.download();
 }
 
 int agnpy_b200_ssc_sed_host(int n_models, const agnpy_model_t* models, int ne_kind,
@@ -260,34 +330,23 @@ int agnpy_b200_ssc_sed_host(int n_models, const agnpy_model_t* models, int ne_ki
                             const double* gamma, int n_gamma, const double* ne_table,
                             const double* ssa_table, int ssa, int integ, double* sed) {
     if (int rc = need_device()) return rc;
-    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || n_seed < 2)
-        return fail(AGNPY_ERR_ARG, "ssc_sed_host: bad sizes");
-    cudaStream_t st = host_stream();
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || n_seed < 2 || !models || !nu || !nu_seed ||
+        !gamma || !sed)
+        return fail(AGNPY_ERR_ARG, "ssc_sed_host: bad sizes or null pointer");
     size_t out_n = (size_t)n_models * n_nu;
-    size_t bytes = pad(sizeof(agnpy_model_t) * n_models) + pad(8 * (size_t)n_nu) +
-                   pad(8 * (size_t)n_seed) + 3 * pad(8 * (size_t)n_gamma) + pad(8 * out_n) + 4096;
-    void* base = io_arena(bytes);
-    if (!base) return fail(AGNPY_ERR_NOMEM, "ssc_sed_host: device memory");
-    Arena a(base);
-    agnpy_model_t* d_models = a.take<agnpy_model_t>(n_models);
-    double* d_nu = a.take<double>(n_nu);
-    double* d_seed = a.take<double>(n_seed);
-    double* d_gamma = a.take<double>(n_gamma);
-    double* d_net = ne_table ? a.take<double>(n_gamma) : nullptr;
-    double* d_sat = ssa_table ? a.take<double>(n_gamma) : nullptr;
-    double* d_sed = a.take<double>(out_n);
-    H2D(d_models, models, n_models, agnpy_model_t);
-    H2D(d_nu, nu, n_nu, double);
-    H2D(d_seed, nu_seed, n_seed, double);
-    H2D(d_gamma, gamma, n_gamma, double);
-    H2D(d_net, ne_table, n_gamma, double);
-    H2D(d_sat, ssa_table, n_gamma, double);
-    if (int rc = agnpy_b200_ssc_sed(n_models, d_models, ne_kind, d_nu, n_nu, d_seed, n_seed, d_gamma,
-                                    n_gamma, d_net, d_sat, ssa, integ, d_sed, st))
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_sd = io.in(nu_seed, 8 * (size_t)n_seed), i_g = io.in(gamma, 8 * (size_t)n_gamma);
+    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma), i_sa = io.in(ssa_table, 8 * (size_t)n_gamma);
+    int o_sed = io.out(sed, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_ssc_sed(n_models, io.dev<agnpy_model_t>(i_m), ne_kind, io.dev<double>(i_nu),
+                                    n_nu, io.dev<double>(i_sd), n_seed, io.dev<double>(i_g), n_gamma,
+                                    io.dev<double>(i_ne), io.dev<double>(i_sa), ssa, integ,
+                                    io.dev<double>(o_sed), io.st))
         return rc;
-    D2H(sed, d_sed, out_n, double);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return check_last("ssc_sed_host");
-    return AGNPY_OK;
+    return io.download();
 }
 
 int agnpy_b200_ec_sed_host(int variant, int n_models, const agnpy_model_t* models, int ne_kind,
@@ -295,34 +354,23 @@ int agnpy_b200_ec_sed_host(int variant, int n_models, const agnpy_model_t* model
                            const double* mu, int n_mu, const double* phi, int n_phi,
                            const double* ne_table, int integ, double* sed) {
     if (int rc = need_device()) return rc;
-    if (n_models < 1 || n_nu < 1 || n_gamma < 2) return fail(AGNPY_ERR_ARG, "ec_sed_host: bad sizes");
-    cudaStream_t st = host_stream();
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || !models || !nu || !gamma || !sed)
+        return fail(AGNPY_ERR_ARG, "ec_sed_host: bad sizes or null pointer");
     size_t out_n = (size_t)n_models * n_nu;
-    size_t bytes = pad(sizeof(agnpy_model_t) * n_models) + pad(8 * (size_t)n_nu) +
-                   2 * pad(8 * (size_t)n_gamma) + pad(8 * (size_t)std::max(n_mu, 1)) +
-                   pad(8 * (size_t)std::max(n_phi, 1)) + pad(8 * out_n) + 4096;
-    void* base = io_arena(bytes);
-    if (!base) return fail(AGNPY_ERR_NOMEM, "ec_sed_host: device memory");
-    Arena a(base);
-    agnpy_model_t* d_models = a.take<agnpy_model_t>(n_models);
-    double* d_nu = a.take<double>(n_nu);
-    double* d_gamma = a.take<double>(n_gamma);
-    double* d_mu = mu ? a.take<double>(n_mu) : nullptr;
-    double* d_phi = phi ? a.take<double>(n_phi) : nullptr;
-    double* d_net = ne_table ? a.take<double>(n_gamma) : nullptr;
-    double* d_sed = a.take<double>(out_n);
-    H2D(d_models, models, n_models, agnpy_model_t);
-    H2D(d_nu, nu, n_nu, double);
-    H2D(d_gamma, gamma, n_gamma, double);
-    H2D(d_mu, mu, n_mu, double);
-    H2D(d_phi, phi, n_phi, double);
-    H2D(d_net, ne_table, n_gamma, double);
-    if (int rc = agnpy_b200_ec_sed(variant, n_models, d_models, ne_kind, d_nu, n_nu, d_gamma, n_gamma,
-                                   d_mu, n_mu, d_phi, n_phi, d_net, integ, d_sed, st))
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma);
+    int i_mu = io.in(mu, 8 * (size_t)(n_mu > 0 ? n_mu : 0)), i_ph = io.in(phi, 8 * (size_t)(n_phi > 0 ? n_phi : 0));
+    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int o_sed = io.out(sed, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_ec_sed(variant, n_models, io.dev<agnpy_model_t>(i_m), ne_kind,
+                                   io.dev<double>(i_nu), n_nu, io.dev<double>(i_g), n_gamma,
+                                   io.dev<double>(i_mu), n_mu, io.dev<double>(i_ph), n_phi,
+                                   io.dev<double>(i_ne), integ, io.dev<double>(o_sed), io.st))
         return rc;
-    D2H(sed, d_sed, out_n, double);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return check_last("ec_sed_host");
-    return AGNPY_OK;
+    return io.download();
 }
 
 int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
@@ -330,32 +378,21 @@ int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
                         const double* phi, int n_phi, const double* l_unit, int n_l,
                         double* tau) {
     if (int rc = need_device()) return rc;
-    if (n_models < 1 || n_nu < 1 || n_phi < 2 || n_l < 2) return fail(AGNPY_ERR_ARG, "tau_host: bad sizes");
-    cudaStream_t st = host_stream();
+    if (n_models < 1 || n_nu < 1 || n_phi < 2 || n_l < 2 || !models || !nu || !phi || !l_unit || !tau)
+        return fail(AGNPY_ERR_ARG, "tau_host: bad sizes or null pointer");
     size_t out_n = (size_t)n_models * n_nu;
-    size_t bytes = pad(sizeof(agnpy_model_t) * n_models) + pad(8 * (size_t)n_nu) +
-                   pad(8 * (size_t)std::max(n_a, 1)) + pad(8 * (size_t)n_phi) + pad(8 * (size_t)n_l) +
-                   pad(8 * out_n) + 4096;
-    void* base = io_arena(bytes);
-    if (!base) return fail(AGNPY_ERR_NOMEM, "tau_host: device memory");
-    Arena a(base);
-    agnpy_model_t* d_models = a.take<agnpy_model_t>(n_models);
-    double* d_nu = a.take<double>(n_nu);
-    double* d_mu = mu ? a.take<double>(n_a) : nullptr;
-    double* d_phi = a.take<double>(n_phi);
-    double* d_l = a.take<double>(n_l);
-    double* d_tau = a.take<double>(out_n);
-    H2D(d_models, models, n_models, agnpy_model_t);
-    H2D(d_nu, nu, n_nu, double);
-    H2D(d_mu, mu, n_a, double);
-    H2D(d_phi, phi, n_phi, double);
-    H2D(d_l, l_unit, n_l, double);
-    if (int rc = agnpy_b200_tau(variant, n_models, d_models, d_nu, n_nu, d_mu, n_a, d_phi, n_phi, d_l,
-                                n_l, d_tau, st))
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_mu = io.in(mu, 8 * (size_t)(n_a > 0 ? n_a : 0)), i_ph = io.in(phi, 8 * (size_t)n_phi);
+    int i_l = io.in(l_unit, 8 * (size_t)n_l);
+    int o_tau = io.out(tau, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_tau(variant, n_models, io.dev<agnpy_model_t>(i_m), io.dev<double>(i_nu), n_nu,
+                                io.dev<double>(i_mu), n_a, io.dev<double>(i_ph), n_phi,
+                                io.dev<double>(i_l), n_l, io.dev<double>(o_tau), io.st))
         return rc;
-    D2H(tau, d_tau, out_n, double);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return check_last("tau_host");
-    return AGNPY_OK;
+    return io.download();
 }
 
 }  // extern "C"

@@ -35,9 +35,12 @@ def integrator_code(integrator):
 
 
 def as_grid(x, name, ascending=True):
-    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 1 and x.flags.c_contiguous:
+        a = x
+    else:
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
     if a.size < 2:
         raise ValueError(f"{name}: need at least 2 grid points")
-    if ascending and not np.all(np.diff(a) > 0):
+    if ascending and not (a[1:] > a[:-1]).all():
         raise ValueError(f"{name}: grid must be strictly ascending")
     return a

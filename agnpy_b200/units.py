@@ -8,6 +8,7 @@ implements the subset of the protocol the hot path touches: `.to_value(unit)`, `
 `.unit`, `.value`, scalar/array arithmetic.  Unit stripping mirrors
 agnpy/utils/conversion.py:30-46: everything ends up as CGS (Gaussian) doubles.
 """
+import functools
 import re
 from fractions import Fraction
 
@@ -52,6 +53,7 @@ _UNITS = {
 _TOKEN = re.compile(r"\s*(/|\*|1(?![0-9])|[A-Za-z_]+)\s*(\(\s*[-+]?\d+(?:/\d+)?\s*\)|[-+]?\d+)?")
 
 
+@functools.lru_cache(maxsize=512)
 def _parse(text):
     """'erg cm-2 s-1', 'erg/s', 'g / s', 'cm(-1/2) g(1/2) s-1' -> (scale, dimension)"""
     text = text.strip()
@@ -130,7 +132,13 @@ class Unit:
         return Unit(f"({self.text})^{p}", (self.scale ** float(p), tuple(a * p for a in self.dim)))
 
     def factor_to(self, other):
-        other = other if isinstance(other, Unit) else Unit(other)
+        if isinstance(other, str):
+            if other == self.text:
+                return 1.0
+            o_scale, o_dim = _parse(other)
+            if self.dim != o_dim:
+                raise UnitConversionError(f"'{self.text}' and '{other}' are not convertible")
+            return self.scale / o_scale
         if self.dim != other.dim:
             raise UnitConversionError(f"'{self.text}' and '{other.text}' are not convertible")
         return self.scale / other.scale
