@@ -12,7 +12,8 @@ namespace agb {
 constexpr size_t kChunkBytes = (size_t)1 << 30;  // scratch budget per batch chunk
 
 static bool bad_kind(int k) { return k < AGNPY_NE_POWERLAW || k > AGNPY_NE_TABLE; }
-static bool bad_integ(int i) { return i != AGNPY_INTEG_TRAPZ && i != AGNPY_INTEG_LOGLOG; }
+static bool bad_integ(int i) { return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_PREFIX; }
+static int plain_integ(int i) { return i == AGNPY_INTEG_TRAPZ_PREFIX ? AGNPY_INTEG_TRAPZ : i; }
 
 static int chunk_models(size_t bytes_per_model, int n_models) {
     size_t c = kChunkBytes / std::max<size_t>(bytes_per_model, 1);
@@ -72,6 +73,7 @@ int agnpy_b200_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
     if (n_nu > 65535) return fail(AGNPY_ERR_ARG, "synch_sed: n_nu > 65535");
     if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table || (ssa && !ssa_table)))
         return fail(AGNPY_ERR_ARG, "synch_sed: AGNPY_NE_TABLE needs n_models == 1 and tables");
+    integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = 3 * (size_t)n_gamma * sizeof(double);
     int chunk = chunk_models(per, n_models);
@@ -103,6 +105,7 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
     if (n_nu > 65535 || n_seed > 65535) return fail(AGNPY_ERR_ARG, "ssc_sed: n_nu/n_seed > 65535");
     if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table || (ssa && !ssa_table)))
         return fail(AGNPY_ERR_ARG, "ssc_sed: AGNPY_NE_TABLE needs n_models == 1 and tables");
+    integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = (3 * (size_t)n_gamma + 2 * (size_t)n_seed) * sizeof(double);
     int chunk = chunk_models(per, n_models);

@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(256) ssc_kernel(
     double* s_c1 = s_lh + n_gamma;
     double* s_qlo = s_c1 + n_gamma;    // q_min (1+guard): surely inside above this
     double* s_qlo2 = s_qlo + n_gamma;  // q_min (1-guard): surely outside below this
-    double* s_Y = s_qlo2 + n_gamma;    // loglog only: [n_seed] gamma-integrals
+    double* s_idl = s_qlo2 + n_gamma;  // loglog only: 1/(ln g_k - ln g_k+1)
+    double* s_lr = s_idl + n_gamma;    // loglog only: ln(g_k+1/g_k)
+    double* s_Y = s_lr + n_gamma;      // loglog only: [n_seed] gamma-integrals
     for (int k = threadIdx.x; k < n_gamma; k += blockDim.x) {
         double g = gs[k];
         double f = Ne[k] / (g * g);
@@ -227,6 +229,11 @@ __global__ void __launch_bounds__(256) ssc_kernel(
         s_c1[k] = 1.0 + 0.5 * (v * v) / (1.0 + v);
         s_qlo[k] = qmin * (1.0 + kGuard);
         s_qlo2[k] = qmin * (1.0 - kGuard);
+        if (INTEG == AGNPY_INTEG_LOGLOG && k < n_gamma - 1) {
+            double gu = gs[k + 1];
+            s_idl[k] = 1.0 / (clipped_log(g) - clipped_log(gu));
+            s_lr[k] = clipped_log(gu / g);
+        }
     }
     __syncthreads();
     const double* Us = U_seed + (size_t)m * n_seed;
@@ -271,8 +278,10 @@ __global__ void __launch_bounds__(256) ssc_kernel(
                         y = in ? f * F : 0.0;
                     }
                 }
-                double ly = clipped_log(y);
-                if (k > 0) acc += loglog_interval(s_g[k - 1], s_g[k], y_prev, y, ly_prev, ly);
+                double ly = (y != 0.0) ? clipped_log(y) : 0.0;
+                if (k > 0)
+                    acc += loglog_interval_pre(s_g[k - 1], s_g[k], s_idl[k - 1], s_lr[k - 1], y_prev, y,
+                                               ly_prev, ly);
                 y_prev = y;
                 ly_prev = ly;
             }
@@ -299,7 +308,8 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
                const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,
                int n_seed, int integ, double* out, cudaStream_t stream) {
     dim3 grid(n_nu, n_models);
-    size_t smem = (7 * (size_t)n_gamma + (integ == AGNPY_INTEG_LOGLOG ? n_seed : 0)) * sizeof(double);
+    size_t smem = (integ == AGNPY_INTEG_LOGLOG ? 9 * (size_t)n_gamma + n_seed : 7 * (size_t)n_gamma) *
+                  sizeof(double);
     if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for ssc kernel");
     if (integ == AGNPY_INTEG_TRAPZ) {
         if (smem > 48 * 1024)

@@ -149,6 +149,9 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
 #pragma unroll
         for (int q = 0; q < kTauTN; ++q) {
             double s = e1[q] * p * h;  // == eps_1 * eps * (1 - cos psi) / 2, same rounding
+            // below the pair-production threshold sigma is exactly 0 (targets_absorption.py:41):
+            // skip the sqrt/log when no lane of the warp is above it (NaN s keeps the slow path)
+            if (__all_sync(__activemask(), s < 1.0 && W == W && fabs(W) <= kFmax)) continue;
             double v = sigma_shape(s, ic * ie1[q]);
             acc[q] = fma(W, v, acc[q]);
         }

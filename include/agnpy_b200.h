@@ -42,6 +42,10 @@ extern "C" {
 /* integrators: the `integrator=` keyword of every evaluate_* */
 #define AGNPY_INTEG_TRAPZ 0  /* numpy.trapz */
 #define AGNPY_INTEG_LOGLOG 1 /* agnpy/utils/math.py:55-119 trapz_loglog */
+/* numpy.trapz evaluated through suffix sums over gamma (external Compton only; the other entry
+ * points treat it as AGNPY_INTEG_TRAPZ).  Same integral, grid and masks; the gamma sum is
+ * re-associated (differences ~1e-15).  Opt-in: see DESIGN.md section 4. */
+#define AGNPY_INTEG_TRAPZ_PREFIX 2
 
 /* external-Compton targets: agnpy/compton/external_compton.py */
 #define AGNPY_EC_ISO_MONO 0      /* :63-142   tgt = {epsilon_0, u_0}                              */
