@@ -297,6 +297,64 @@ def run_cuda(args):
         one()
     single_us = (time.perf_counter() - t0) / 50 * 1e6
 
+    # ---- secondary figures (same run, device-resident, CUDA events) ---------------------------
+    def timed(plan_x, dm, dout, reps):
+        for _ in range(3):
+            plan_x.launch(dm, dout)
+        torch.cuda.synchronize()
+        _lib.kernel_timing(True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            plan_x.launch(dm, dout)
+        b.record()
+        torch.cuda.synchronize()
+        km, kk = _lib.kernel_timing_read()
+        _lib.kernel_timing(False)
+        return a.elapsed_time(b) / reps, km / max(kk, 1)
+
+    # (a) the opt-in suffix-sum evaluation of np.trapz on the same batch
+    plan_fast = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"],
+                         phi=g["phi"], integrator="trapz_prefix", device=dev)
+    fast_ms, fast_kms = timed(plan_fast, d_models, d_out, max(3, min(args.steps, 10)))
+    fast_dev, _ = cases.max_rel_dev(d_out[0].cpu().numpy()[::8], chk)
+    # (b) SSC at BASELINE configs[0] grids (tutorial blob, 100 nu x 200 seeds x 200 gamma)
+    c1 = cases.case_c1()
+    ssc_models = _lib.make_models(MODELS_PER_GPU)
+    rng = np.random.default_rng(1)
+    for i in range(MODELS_PER_GPU):
+        from agnpy_b200 import _core
+        _core.model_row(ssc_models, i, z=c1["z"], d_L=c1["d_L"], delta_D=rng.uniform(5, 30),
+                        B=10 ** rng.uniform(-1.5, 0.5), R_b=10 ** rng.uniform(15.5, 16.5),
+                        ne=[10 ** rng.uniform(-9, -7), rng.uniform(1.5, 2.5), rng.uniform(2.6, 4),
+                            10 ** rng.uniform(3.5, 5), 10.0, 1e6, 0, 0])
+    plan_ssc = SedBatch("ssc", c1["nu"], "BrokenPowerLaw", gamma=c1["gamma"], device=dev)
+    d_ssc = torch.from_numpy(np.ascontiguousarray(ssc_models).view(np.float64)
+                             .reshape(MODELS_PER_GPU, -1).copy()).to(dev)
+    d_ssc_out = torch.empty(MODELS_PER_GPU, c1["nu"].size, dtype=torch.float64, device=dev)
+    ssc_ms, ssc_kms = timed(plan_ssc, d_ssc, d_ssc_out, max(3, min(args.steps, 10)))
+    from oracle import agnpy_oracle as orc
+    m0 = ssc_models[0]
+    ssc_ref = orc.ssc_sed_flux(c1["nu"], m0["z"], m0["d_L"], m0["delta_D"], m0["B"], m0["R_b"],
+                               "BrokenPowerLaw", tuple(m0["ne"][:6]), gamma=c1["gamma"])
+    ssc_dev, _ = cases.max_rel_dev(d_ssc_out[0].cpu().numpy(), ssc_ref)
+    ssc_pts = MODELS_PER_GPU * (100 * 200 * 200)
+    extra = {
+        "ec_blr_trapz_prefix": {
+            "value": len(local) / (fast_ms * 1e-3), "unit": UNIT, "ms_per_step": fast_ms,
+            "kernel": "ec_prefix_kernel", "kernel_ms": fast_kms, "parity_max_rel_dev": fast_dev,
+            "note": "opt-in integrator=trapz_prefix: np.trapz over gamma through suffix sums, same "
+                    "integral / grid / masks (DESIGN.md section 4); not the headline"},
+        "ssc_config1": {
+            "value": MODELS_PER_GPU / (ssc_ms * 1e-3), "unit": UNIT, "ms_per_step": ssc_ms,
+            "workload": "configs[0]: SSC of the tutorial blob, 100 nu x 200 seed nu x 200 gamma, "
+                        "np.trapz, 256 models per step (seed synchrotron spectrum included)",
+            "kernel": "ssc_kernel<trapz>", "kernel_ms": ssc_kms,
+            "integrand_gpts_per_s": ssc_pts / (ssc_ms * 1e-3) / 1e9,
+            "roofline_frac_algorithmic": ssc_pts * 24 / (ssc_kms * 1e-3) / peak,
+            "algorithmic_flops_per_point": 24, "parity_max_rel_dev": ssc_dev},
+    }
+
     # CPU baseline: the oracle (reference arithmetic), 1 core, bounded sample
     t0 = time.perf_counter()
     n_cpu = 0
@@ -348,6 +406,7 @@ def run_cuda(args):
                                    "arithmetic, nu-chunked by 25), 1 thread",
                          "host_cpus": os.cpu_count()},
         "clocks": clocks,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

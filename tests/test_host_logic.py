@@ -159,3 +159,24 @@ def test_targets_and_blob_containers():
     assert blob.gamma_e[0] == pytest.approx(10) and blob.gamma_e_external_frame.size == 200
     with pytest.raises(ValueError):
         ab.Absorption(blr)  # r is mandatory, targets_absorption.py:68-73
+
+
+def test_fit_parameter_marshalling():
+    """sherpa-wrapper parameter order and log10 scaling (fit/sherpa_wrapper.py:29-75, 228-275)"""
+    from agnpy_b200 import constants as const, fit
+    pars = np.array([[-8.0, 2.0, 3.5, 4.0, np.log10(20), np.log10(5e7), 1.0, 40.0, -0.5, 86400.0, 0.9997,
+                      18.0, np.log10(2e46), 2.4e42, 1e26, 1e15, 1e17, 0.024, 1215.67, 1e17, 0.1, 1e3,
+                      1.5e19]] * 2)
+    m = fit.build_models(pars, 2.0957e28, "BrokenPowerLaw", "ec_blr_dt")
+    assert set(m) == {"synch", "ssc", "ec_blr", "ec_dt"}
+    b = m["ec_blr"][1]
+    assert b["B"] == pytest.approx(10 ** -0.5) and b["mu_s"] == 0.9997 and m["synch"][0]["mu_s"] == 1.0
+    assert b["R_b"] == pytest.approx(const.c * 86400.0 * 40 / 2)
+    np.testing.assert_allclose(b["ne"][:6], [1e-8, 2.0, 3.5, 1e4, 20, 5e7], rtol=1e-14)
+    np.testing.assert_allclose(b["tgt"][:5], [2e46, 0.024, 1.9958625603e-05, 1e17, 1e18], rtol=1e-9)
+    np.testing.assert_allclose(m["ec_dt"][0]["tgt"][:5],
+                               [2e46, 0.1, 2.7 * const.k_B * 1e3 / const.mec2, 1.5e19, 1e18], rtol=1e-12)
+    with pytest.raises(ValueError):
+        fit.build_models(pars[:, :12], 1e28, "BrokenPowerLaw", "ec_blr_dt")
+    ecbpl = fit.scale_spectral_parameters(np.array([[-8, 2, 3, 5.0, 4.0, 1.0, 7.0]]), "ExpCutoffBrokenPowerLaw")
+    np.testing.assert_allclose(ecbpl[0], [1e-8, 2, 3, 1e5, 1e4, 10, 1e7])
