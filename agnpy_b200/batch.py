@@ -61,6 +61,31 @@ def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu"):
     return out[:n]
 
 
+def nu_slice(n_nu, world_size, rank):
+    """[lo, hi) of the frequencies owned by `rank` and the padded per-rank count (config 4:
+    the nu grid is sharded, every other grid is replicated)"""
+    return local_slice(n_nu, world_size, rank)
+
+
+def nu_sharded_evaluate(local_compute, nu, n_models, group=None, device="cpu"):
+    """Frequency sharding: `local_compute(nu[lo:hi]) -> tensor [n_models, hi-lo]` on this rank's
+    slice of the frequency grid, then ONE all-gather; returns [n_models, n_nu] on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return local_compute(nu)
+    rank = dist.get_rank(group)
+    n = len(nu)
+    lo, hi, per_rank = nu_slice(n, world, rank)
+    block = torch.zeros(per_rank, n_models, dtype=torch.float64, device=device)  # [nu, model]
+    if hi > lo:
+        block[: hi - lo] = local_compute(nu[lo:hi]).transpose(0, 1)
+    out = torch.empty(world * per_rank, n_models, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    return out[:n].transpose(0, 1).contiguous()
+
+
 # ---- the GPU plan -----------------------------------------------------------------------------
 class SedBatch:
     """One radiative process on fixed grids, evaluated for batches of models on one GPU
@@ -68,7 +93,7 @@ class SedBatch:
 
     def __init__(self, process, nu, ne_kind="BrokenPowerLaw", *, gamma=None, mu=None, phi=None,
                  nu_seed=None, mu_size=100, l_size=50, ssa=False, integrator="trapz",
-                 device=None, group=None):
+                 device=None, group=None, shard="models"):
         import torch
         from . import grids
         if process not in PROCESSES:
@@ -80,6 +105,18 @@ class SedBatch:
         self.process = process
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.group = group
+        if shard not in ("models", "nu"):
+            raise ValueError("shard must be 'models' or 'nu'")
+        self.shard = shard
+        self.nu_full = np.ascontiguousarray(np.ravel(nu), dtype=np.float64)
+        if shard == "nu":  # this rank keeps only its slice of the frequency grid on the device
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                lo, hi, _ = nu_slice(self.nu_full.size, dist.get_world_size(group), dist.get_rank(group))
+                nu = self.nu_full[lo:hi] if hi > lo else self.nu_full[:1]
+                self._nu_empty = hi <= lo
+            else:
+                self._nu_empty = False
         self.ne_kind = _NE_KINDS[ne_kind] if isinstance(ne_kind, str) else int(ne_kind)
         self.integ = grids.integrator_code(integrator)
         self.ssa = int(bool(ssa))
@@ -149,6 +186,10 @@ class SedBatch:
 
     def evaluate_device(self, models):
         """as __call__ but returns the (gathered) device tensor without the D2H copy"""
+        if self.shard == "nu":
+            def local(nu_part):  # the plan already holds this rank's slice
+                return self._local(models)[:, : len(nu_part)]
+            return nu_sharded_evaluate(local, self.nu_full, len(models), self.group, self.device)
         return sharded_evaluate(self._local, models, self.n_nu, self.group, self.device)
 
     def __call__(self, models):
@@ -157,9 +198,9 @@ class SedBatch:
         torch = self.torch
         with torch.cuda.device(self.device):
             out = self.evaluate_device(models)
-            n = out.shape[0]
-            if self._pinned_out is None or self._pinned_out.shape[0] < n:
-                self._pinned_out = torch.empty(n, self.n_nu, dtype=torch.float64).pin_memory()
+            n, w = out.shape
+            if self._pinned_out is None or self._pinned_out.shape[0] < n or self._pinned_out.shape[1] != w:
+                self._pinned_out = torch.empty(n, w, dtype=torch.float64).pin_memory()
             host = self._pinned_out[:n]
             host.copy_(out, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from agnpy_b200 import _core, _lib
-from agnpy_b200.batch import local_slice, partition, sharded_evaluate
+from agnpy_b200.batch import local_slice, nu_sharded_evaluate, partition, sharded_evaluate
 
 
 def test_partition_arithmetic():
@@ -74,3 +74,36 @@ def test_sharded_evaluate_world2_gloo(n_models):
     for r in range(2):
         assert results[r].shape == (n_models, nu.size)
         np.testing.assert_array_equal(results[r], full)   # every rank holds the whole batch
+
+
+def _nu_worker(rank, world, port, n_nu, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nu = np.logspace(9, 18, n_nu)
+    models = _models(3)
+    out = nu_sharded_evaluate(lambda part: _cpu_compute(part)(models), nu, len(models), device="cpu")
+    q.put((rank, out.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_nu", [9, 8, 1])
+def test_nu_sharded_evaluate_world2_gloo(n_nu):
+    """BASELINE config 4 style frequency sharding: slices, padding, gather order"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nu_worker, args=(r, 2, port, n_nu, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nu = np.logspace(9, 18, n_nu)
+    full = _cpu_compute(nu)(_models(3)).numpy()
+    for r in range(2):
+        assert results[r].shape == (3, n_nu)
+        np.testing.assert_array_equal(results[r], full)
