@@ -1,0 +1,188 @@
+"""Edge cases of the drop-in boundary on the GPU: minimal and ragged sizes, empty electron
+distributions, unsorted / repeated frequencies, scalar-like inputs, random parameter sweeps
+against the oracle, argument errors."""
+import numpy as np
+import pytest
+
+import agnpy_b200 as ab
+from agnpy_b200 import _lib, spectra, u
+from oracle import agnpy_oracle as orc
+from tests import cases
+from tests.test_gpu_parity import assert_parity, ec_args, ne_obj, ne_tail, q_args
+
+pytestmark = pytest.mark.gpu
+ERG = u.Unit("erg s-1")
+
+
+def blr_call(c, **kw):
+    return ab.ExternalCompton.evaluate_sed_flux_blr(
+        *ec_args(c), c["L_disk"] * ERG, c["xi_line"], c["epsilon_line"], c["R_line"] * u.cm,
+        c["r"] * u.cm, *ne_tail(c), gamma=c["gamma"], mu=c["mu"], phi=c["phi"], **kw).value
+
+
+def test_minimal_grids():
+    """2-point grids on every axis and a single frequency"""
+    c = cases.case_c2(n_nu=1, n_gamma=2, n_mu=2, n_phi=2, r=2e17)
+    c["nu"] = np.array([1e22])
+    c["gamma"] = np.array([1e3, 1e5])
+    for integ, integrator in (("trapz", np.trapezoid), ("trapz_loglog", ab.trapz_loglog),
+                              ("trapz", ab.trapz_prefix)):
+        got = blr_call(c, integrator=integrator)
+        ref = cases.ORACLE_EC["blr"](c, integ)
+        assert got.shape == (1,)
+        if ref[0] == 0:
+            assert got[0] == 0
+        else:
+            assert abs(got[0] / ref[0] - 1) < 1e-9
+
+
+def test_unsorted_and_repeated_frequencies_keep_shape():
+    c = cases.case_c2(n_nu=16, r=1e18)
+    rng = np.random.default_rng(3)
+    nu = rng.permutation(np.concatenate([c["nu"], c["nu"][:4]]))
+    c2 = dict(c, nu=nu)
+    got = blr_call(c2)
+    assert_parity(got, cases.ORACLE_EC["blr"](c2), what="unsorted nu")
+    nu2d = nu.reshape(4, 5)
+    got2 = ab.ExternalCompton.evaluate_sed_flux_blr(
+        nu2d * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["mu_s"], c["R_b"] * u.cm,
+        c["L_disk"] * ERG, c["xi_line"], c["epsilon_line"], c["R_line"] * u.cm, c["r"] * u.cm,
+        *ne_tail(c), gamma=c["gamma"], mu=c["mu"], phi=c["phi"])
+    assert got2.shape == (4, 5)
+    np.testing.assert_array_equal(got2.value.ravel(), got)
+
+
+def test_electrons_outside_the_gamma_grid_give_exact_zeros():
+    """n_e = 0 on the whole integration grid: every entry point returns exact zeros"""
+    args = (1e-8, 2.0, 1e10, 1e11)            # above logspace(1, 9)
+    ne = spectra.PowerLaw(*args)
+    nu = np.logspace(10, 28, 12) * u.Hz
+    common = (nu, 0.1, 1e27 * u.cm, 10.0)
+    for integrator in (np.trapezoid, ab.trapz_loglog):
+        s = ab.Synchrotron.evaluate_sed_flux(*common, 1 * u.G, 1e16 * u.cm, ne, *q_args(args),
+                                             integrator=integrator, ssa=True)
+        assert np.all(s.value == 0)
+        s = ab.SynchrotronSelfCompton.evaluate_sed_flux(*common, 1 * u.G, 1e16 * u.cm, ne,
+                                                        *q_args(args), integrator=integrator)
+        assert np.all(s.value == 0)
+        s = ab.ExternalCompton.evaluate_sed_flux_dt(*common, 0.99, 1e16 * u.cm, 1e45 * ERG, 0.1, 1e-6,
+                                                    1e18 * u.cm, 1e17 * u.cm, ne, *q_args(args),
+                                                    integrator=integrator)
+        assert np.all(s.value == 0)
+    s = ab.ExternalCompton.evaluate_sed_flux_blr(*common, 0.99, 1e16 * u.cm, 1e45 * ERG, 0.1, 2e-5,
+                                                 1e17 * u.cm, 1e18 * u.cm, ne, *q_args(args),
+                                                 integrator=ab.trapz_prefix)
+    assert np.all(s.value == 0)
+
+
+def test_frequencies_beyond_the_kinematic_limit_are_exact_zeros():
+    c = cases.case_c2(n_nu=12, r=1e18)
+    c["nu"] = np.logspace(31, 34, 12)          # eps_s > gamma_max delta_D: nothing can scatter there
+    for integrator in (np.trapezoid, ab.trapz_loglog, ab.trapz_prefix):
+        assert np.all(blr_call(c, integrator=integrator) == 0)
+    t = ab.Absorption.evaluate_tau_blr(np.logspace(18, 21, 8) * u.Hz, 0.5, 1.0, 2e46 * ERG, 0.024,
+                                       cases.EPS_LINE, 1e17 * u.cm, 1e16 * u.cm)
+    assert np.all(t == 0)                       # below the pair-production threshold
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_parameter_sweep_against_oracle(seed):
+    """random physical parameters in (and beyond) the fit ranges of fit/core.py:92-157"""
+    rng = np.random.default_rng(1000 + seed)
+    kind = ["PowerLaw", "BrokenPowerLaw", "LogParabola", "ExpCutoffPowerLaw",
+            "ExpCutoffBrokenPowerLaw"][seed % 5]
+    gmin, gmax = 10 ** rng.uniform(0.5, 2.5), 10 ** rng.uniform(5, 8)
+    shape = {"PowerLaw": (rng.uniform(1.5, 3.5),),
+             "BrokenPowerLaw": (rng.uniform(1.5, 2.5), rng.uniform(2.6, 4.5), 10 ** rng.uniform(3, 5)),
+             "LogParabola": (rng.uniform(1.5, 3), rng.uniform(0.05, 0.6), 10 ** rng.uniform(2.5, 4.5)),
+             "ExpCutoffPowerLaw": (rng.uniform(1.5, 3), 10 ** rng.uniform(3.5, 6)),
+             "ExpCutoffBrokenPowerLaw": (rng.uniform(1.5, 2.5), rng.uniform(2.6, 4), 10 ** rng.uniform(4, 6),
+                                         10 ** rng.uniform(3, 4.5))}[kind]
+    args = (10 ** rng.uniform(-9, -5),) + shape + (gmin, gmax)
+    z, delta = rng.uniform(0.01, 2.5), rng.uniform(2, 50)
+    Gamma = rng.uniform(max(2.0, delta / 2), delta * 1.2)
+    beta = np.sqrt(1 - 1 / Gamma**2)
+    mu_s = float(np.clip((1 - 1 / (Gamma * delta)) / beta, -1, 1))
+    d_L, R_b, B = 10 ** rng.uniform(26.5, 28.5), 10 ** rng.uniform(15, 17), 10 ** rng.uniform(-2, 1)
+    nu = np.logspace(rng.uniform(8, 12), rng.uniform(24, 30), 28)
+    gamma = np.logspace(np.log10(gmin), np.log10(gmax), int(rng.integers(40, 260)))
+    ne = ne_obj(kind, args)
+    integ, integrator = (("trapz", np.trapezoid), ("trapz_loglog", ab.trapz_loglog))[seed % 2]
+    got = ab.Synchrotron.evaluate_sed_flux(nu * u.Hz, z, d_L * u.cm, delta, B * u.G, R_b * u.cm, ne,
+                                           *q_args(args), integrator=integrator, gamma=gamma)
+    assert_parity(got.value, orc.synch_sed_flux(nu, z, d_L, delta, B, R_b, kind, args,
+                                                integrator=integ, gamma=gamma), what="sweep synch")
+    got = ab.SynchrotronSelfCompton.evaluate_sed_flux(nu * u.Hz, z, d_L * u.cm, delta, B * u.G,
+                                                      R_b * u.cm, ne, *q_args(args),
+                                                      integrator=integrator, gamma=gamma)
+    assert_parity(got.value, orc.ssc_sed_flux(nu, z, d_L, delta, B, R_b, kind, args,
+                                              integrator=integ, gamma=gamma), what="sweep ssc")
+    L, xi, R_line, r = 10 ** rng.uniform(44, 47), rng.uniform(0.01, 0.3), 10 ** rng.uniform(16.5, 18), 10 ** rng.uniform(15.5, 19.5)
+    g_ec = np.logspace(1, 9, int(rng.integers(60, 220)))
+    mu, phi = np.linspace(-1, 1, int(rng.integers(11, 60))), np.linspace(0, 2 * np.pi, int(rng.integers(7, 40)))
+    got = ab.ExternalCompton.evaluate_sed_flux_blr(
+        nu * u.Hz, z, d_L * u.cm, delta, mu_s, R_b * u.cm, L * ERG, xi, cases.EPS_LINE, R_line * u.cm,
+        r * u.cm, ne, *q_args(args), integrator=integrator, gamma=g_ec, mu=mu, phi=phi)
+    ref = orc.ec_blr_sed_flux(nu, z, d_L, delta, mu_s, R_b, L, xi, cases.EPS_LINE, R_line, r, kind, args,
+                              integrator=integ, gamma=g_ec, mu=mu, phi=phi)
+    assert_parity(got.value, ref, what="sweep ec blr")
+    if integ == "trapz":
+        got = ab.ExternalCompton.evaluate_sed_flux_blr(
+            nu * u.Hz, z, d_L * u.cm, delta, mu_s, R_b * u.cm, L * ERG, xi, cases.EPS_LINE,
+            R_line * u.cm, r * u.cm, ne, *q_args(args), integrator=ab.trapz_prefix, gamma=g_ec, mu=mu, phi=phi)
+        assert_parity(got.value, ref, what="sweep ec blr prefix")
+    T_dt = rng.uniform(300, 2000)
+    eps_dt, R_dt = orc.dt_epsilon(T_dt), orc.dt_sublimation_radius(L, T_dt)
+    got = ab.ExternalCompton.evaluate_sed_flux_dt(
+        nu * u.Hz, z, d_L * u.cm, delta, mu_s, R_b * u.cm, L * ERG, 0.1, eps_dt, R_dt * u.cm, r * u.cm,
+        ne, *q_args(args), integrator=integrator, gamma=g_ec, phi=phi)
+    assert_parity(got.value, orc.ec_dt_sed_flux(nu, z, d_L, delta, mu_s, R_b, L, 0.1, eps_dt, R_dt, r, kind,
+                                                args, integrator=integ, gamma=g_ec, phi=phi), what="sweep ec dt")
+    nu_tau = np.logspace(24, 30, 20)
+    got = ab.Absorption.evaluate_tau_blr(nu_tau * u.Hz, z, 1.0, L * ERG, xi, cases.EPS_LINE, R_line * u.cm,
+                                         r * u.cm, l_size=33, mu=mu, phi=phi)
+    assert_parity(got, orc.tau_blr(nu_tau, z, 1.0, L, xi, cases.EPS_LINE, R_line, r, l_size=33, mu=mu, phi=phi),
+                  what="sweep tau blr")
+    got = ab.Absorption.evaluate_tau_dt(nu_tau * u.Hz, z, 1.0, L * ERG, 0.1, eps_dt, R_dt * u.cm, r * u.cm,
+                                        l_size=41, phi=phi)
+    assert_parity(got, orc.tau_dt(nu_tau, z, 1.0, L, 0.1, eps_dt, R_dt, r, l_size=41, phi=phi), what="sweep tau dt")
+
+
+def test_argument_errors():
+    ne = spectra.PowerLaw(1e-8, 2.0, 10, 1e5)
+    nu = np.logspace(10, 20, 5) * u.Hz
+    with pytest.raises(ValueError):           # unknown integrator: no host fallback
+        ab.Synchrotron.evaluate_sed_flux(nu, 0.1, 1e27 * u.cm, 10, 1 * u.G, 1e16 * u.cm, ne,
+                                         *ne.parameters, integrator=np.sum)
+    with pytest.raises(TypeError):            # wrong physical dimension
+        ab.Synchrotron.evaluate_sed_flux(nu, 0.1, 1e27 * u.Hz, 10, 1 * u.G, 1e16 * u.cm, ne, *ne.parameters)
+    with pytest.raises(ValueError):           # wrong number of spectral parameters
+        ab.Synchrotron.evaluate_sed_flux(nu, 0.1, 1e27 * u.cm, 10, 1 * u.G, 1e16 * u.cm, ne, 1e-8, 2.0)
+    with pytest.raises(ValueError):           # descending gamma grid
+        ab.Synchrotron.evaluate_sed_flux(nu, 0.1, 1e27 * u.cm, 10, 1 * u.G, 1e16 * u.cm, ne,
+                                         *ne.parameters, gamma=np.logspace(5, 1, 50))
+    # C ABI argument checks
+    L = _lib.lib()
+    assert L.agnpy_b200_ec_sed_host(99, 1, None, 0, None, 1, None, 2, None, 2, None, 2, None, 0, None) != 0
+    assert b"ec_sed" in L.agnpy_b200_last_error()
+    models = _lib.make_models(1)
+    out = np.zeros(3)
+    rc = L.agnpy_b200_tau_host(_lib.TAU_BLR, 1, models.ctypes.data, out.ctypes.data, 3, None, 0,
+                               out.ctypes.data, 3, out.ctypes.data, 3, out.ctypes.data)
+    assert rc == 1 and b"mu grid" in L.agnpy_b200_last_error()
+
+
+def test_units_are_converted_not_assumed():
+    """parsec / Mpc / W / kg inputs give the same SED as their CGS equivalents"""
+    c = cases.case_c3_dt(n_nu=20)
+    ne = ne_tail(c)
+    a = ab.ExternalCompton.evaluate_sed_flux_dt(
+        c["nu"] * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["mu_s"], c["R_b"] * u.cm,
+        c["L_disk"] * ERG, c["xi_dt"], c["epsilon_dt"], c["R_dt"] * u.cm, c["r"] * u.cm, *ne,
+        gamma=c["gamma"], phi=c["phi"])
+    pc = 3.0856775814913673e18
+    b = ab.ExternalCompton.evaluate_sed_flux_dt(
+        c["nu"] / 1e9 * u.GHz, c["z"], c["d_L"] / (1e6 * pc) * u.Mpc, c["delta_D"], c["mu_s"],
+        c["R_b"] / 100 * u.m, c["L_disk"] / 1e7 * u.W, c["xi_dt"], c["epsilon_dt"], c["R_dt"] / pc * u.pc,
+        c["r"] / pc * u.pc, ne[0], ne[1].to("m-3"), *ne[2:], gamma=c["gamma"], phi=c["phi"])
+    np.testing.assert_allclose(a.value, b.value, rtol=1e-12)
