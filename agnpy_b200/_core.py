@@ -65,3 +65,14 @@ def tau_host(variant, models, nu, mu, n_a, phi, l_unit):
         variant, n, hptr(models), hptr(nu), nu.size, hptr(mu), int(n_a), hptr(phi), phi.size,
         hptr(l_unit), l_unit.size, hptr(tau)), "agnpy_b200_tau_host")
     return tau
+
+
+def bb_sed_host(variant, models, nu, nu_norm=None, n_R=100):
+    nu = f64(nu)
+    nu_norm = None if nu_norm is None else f64(nu_norm)
+    n = len(models)
+    sed = np.empty((n, nu.size))
+    check(lib().agnpy_b200_bb_sed_host(
+        variant, n, hptr(models), hptr(nu), nu.size, hptr(nu_norm),
+        0 if nu_norm is None else nu_norm.size, int(n_R), hptr(sed)), "agnpy_b200_bb_sed_host")
+    return sed

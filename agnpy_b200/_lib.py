@@ -17,6 +17,7 @@ NE_EXP_CUTOFF_POWERLAW, NE_EXP_CUTOFF_BROKEN_POWERLAW, NE_TABLE = 3, 4, 5
 INTEG_TRAPZ, INTEG_LOGLOG, INTEG_TRAPZ_PREFIX = 0, 1, 2
 EC_ISO_MONO, EC_PS_BEHIND_JET, EC_SS_DISK, EC_BLR, EC_DT = 0, 1, 2, 3, 4
 TAU_SS_DISK, TAU_BLR, TAU_DT = 0, 1, 2
+BB_DISK, BB_DISK_NORM, BB_DT, BB_DT_NORM = 0, 1, 2, 3
 
 EXPORTS = [
     "agnpy_b200_version", "agnpy_b200_last_error", "agnpy_b200_launch_count",
@@ -25,6 +26,7 @@ EXPORTS = [
     "agnpy_b200_ssc_sed", "agnpy_b200_ssc_sed_host",
     "agnpy_b200_ec_sed", "agnpy_b200_ec_sed_host",
     "agnpy_b200_tau", "agnpy_b200_tau_host",
+    "agnpy_b200_bb_sed", "agnpy_b200_bb_sed_host",
 ]
 
 
@@ -76,6 +78,9 @@ def lib():
     tau = [ip, ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
     L.agnpy_b200_tau.argtypes = tau + [vp]
     L.agnpy_b200_tau_host.argtypes = tau
+    bb = [ip, ip, dp, dp, ip, dp, ip, ip, dp]
+    L.agnpy_b200_bb_sed.argtypes = bb + [vp]
+    L.agnpy_b200_bb_sed_host.argtypes = bb
     L.agnpy_b200_kernel_timing.argtypes = [C.c_int]
     L.agnpy_b200_kernel_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     for name in EXPORTS[3:]:

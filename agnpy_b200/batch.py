@@ -24,7 +24,9 @@ _NE_KINDS = {"PowerLaw": _lib.NE_POWERLAW, "BrokenPowerLaw": _lib.NE_BROKEN_POWE
 _EC = {"ec_iso_mono": _lib.EC_ISO_MONO, "ec_ps_behind_jet": _lib.EC_PS_BEHIND_JET,
        "ec_ss_disk": _lib.EC_SS_DISK, "ec_blr": _lib.EC_BLR, "ec_dt": _lib.EC_DT}
 _TAU = {"tau_ss_disk": _lib.TAU_SS_DISK, "tau_blr": _lib.TAU_BLR, "tau_dt": _lib.TAU_DT}
-PROCESSES = ("synch", "ssc") + tuple(_EC) + tuple(_TAU)
+_BB = {"bb_disk": _lib.BB_DISK, "bb_disk_norm": _lib.BB_DISK_NORM, "bb_dt": _lib.BB_DT,
+       "bb_dt_norm": _lib.BB_DT_NORM}
+PROCESSES = ("synch", "ssc") + tuple(_EC) + tuple(_TAU) + tuple(_BB)
 
 
 # ---- sharding arithmetic (pure; covered by the gloo tests on CPU) ---------------------------
@@ -165,6 +167,10 @@ class SedBatch:
             rc = L.agnpy_b200_ec_sed(v, n, d_models.data_ptr(), self.ne_kind, self.nu.data_ptr(),
                                      self.n_nu, self.gamma.data_ptr(), self.gamma.numel(), mu_ptr,
                                      n_mu, self.phi.data_ptr(), self.phi.numel(), None, self.integ,
+                                     d_out.data_ptr(), st)
+        elif p in _BB:
+            rc = L.agnpy_b200_bb_sed(_BB[p], n, d_models.data_ptr(), self.nu.data_ptr(), self.n_nu,
+                                     self.nu_seed.data_ptr(), self.nu_seed.numel(), 100,
                                      d_out.data_ptr(), st)
         else:
             v = _TAU[p]

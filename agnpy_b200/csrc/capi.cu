@@ -188,6 +188,21 @@ int agnpy_b200_tau(int variant, int n_models, const agnpy_model_t* models, const
     return AGNPY_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+int agnpy_b200_bb_sed(int variant, int n_models, const agnpy_model_t* models, const double* nu,
+                      int n_nu, const double* nu_norm, int n_norm, int n_R, double* sed,
+                      void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (variant < AGNPY_BB_DISK || variant > AGNPY_BB_DT_NORM) return fail(AGNPY_ERR_ARG, "bb_sed: bad variant");
+    if (n_models < 1 || n_nu < 1 || !models || !nu || !sed)
+        return fail(AGNPY_ERR_ARG, "bb_sed: bad sizes or null pointer");
+    if (variant <= AGNPY_BB_DISK_NORM && n_R < 2) return fail(AGNPY_ERR_ARG, "bb_sed: n_R < 2");
+    if (variant == AGNPY_BB_DISK_NORM && (!nu_norm || n_norm < 2))
+        return fail(AGNPY_ERR_ARG, "bb_sed: normalisation frequencies required");
+    return run_bb(variant, models, n_models, nu, n_nu, nu_norm, n_norm, n_R > 0 ? n_R : 2, sed,
+                  (cudaStream_t)stream_);
+}
+
 }  // extern "C"
 
 // ==========================================================================================
@@ -394,6 +409,25 @@ int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
     if (int rc = agnpy_b200_tau(variant, n_models, io.dev<agnpy_model_t>(i_m), io.dev<double>(i_nu), n_nu,
                                 io.dev<double>(i_mu), n_a, io.dev<double>(i_ph), n_phi,
                                 io.dev<double>(i_l), n_l, io.dev<double>(o_tau), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_bb_sed_host(int variant, int n_models, const agnpy_model_t* models,
+                           const double* nu, int n_nu, const double* nu_norm, int n_norm, int n_R,
+                           double* sed) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || !models || !nu || !sed)
+        return fail(AGNPY_ERR_ARG, "bb_sed_host: bad sizes or null pointer");
+    size_t out_n = (size_t)n_models * n_nu;
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_nn = io.in(nu_norm, 8 * (size_t)(n_norm > 0 ? n_norm : 0));
+    int o_sed = io.out(sed, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_bb_sed(variant, n_models, io.dev<agnpy_model_t>(i_m), io.dev<double>(i_nu),
+                                   n_nu, io.dev<double>(i_nn), n_norm, n_R, io.dev<double>(o_sed), io.st))
         return rc;
     return io.download();
 }

@@ -28,4 +28,7 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
             const double* mu, int n_a, const double* phi, int n_phi, const double* l_unit, int n_l,
             double* tau, double* ws, cudaStream_t stream);
 
+int run_bb(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
+           const double* nu_norm, int n_norm, int n_R, double* sed, cudaStream_t stream);
+
 }  // namespace agb

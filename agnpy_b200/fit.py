@@ -1,4 +1,4 @@
-"""Batched fit-level model: the non-thermal components the reference's fit wrappers add up per
+"""Batched fit-level model: the components the reference's fit wrappers add up per
 parameter vector (agnpy/fit/sherpa_wrapper.py:51-75, 228-325; gammapy_wrapper.py:161-181,
 284-357), evaluated for a whole batch of parameter vectors -- an MCMC ensemble, a likelihood
 scan, the trial points of an optimiser -- in one pass, sharded over the GPUs of a box.
@@ -15,8 +15,8 @@ As in the wrappers, Synch and SSC integrate over utils/math.py:6 `gamma_e_to_int
 
 The luminosity distance is an input (`d_L`, cm, one per vector): the reference derives it from z
 with astropy's cosmology per call (sherpa_wrapper.py:63), which is outside the hot path.
-The thermal black-body terms of the wrappers (disk multi-T BB, DT BB) are not part of this
-build yet.
+The EC scenario also adds the two thermal terms of the wrappers: the normalised multi-T
+black body of the disk and the normalised black body of the torus (sherpa_wrapper.py:283-288).
 """
 import numpy as np
 
@@ -77,7 +77,14 @@ def build_models(pars, d_L, ne_kind, scenario):
     dt["mu_s"] = mu_s
     dt["tgt"][:, 0], dt["tgt"][:, 1], dt["tgt"][:, 2] = L_disk, xi_dt, epsilon_dt
     dt["tgt"][:, 3], dt["tgt"][:, 4] = R_dt, r
-    out.update(ec_blr=blr, ec_dt=dt)
+    bb_disk = base.copy()   # SSDisk.evaluate_multi_T_bb_norm_sed(nu, z, L_disk, M_BH, m_dot, R_in, R_out, d_L)
+    bb_disk["mu_s"] = 1.0   # the wrappers use the default mu_s = 1 for the disk SED
+    for k, v in enumerate((M_BH, m_dot, R_in, R_out, L_disk)):
+        bb_disk["tgt"][:, k] = v
+    bb_dt = base.copy()     # RingDustTorus.evaluate_bb_norm_sed(nu, z, xi_dt * L_disk, T_dt, R_dt, d_L)
+    for k, v in enumerate((T_dt, R_dt, xi_dt * L_disk)):
+        bb_dt["tgt"][:, k] = v
+    out.update(ec_blr=blr, ec_dt=dt, bb_disk=bb_disk, bb_dt=bb_dt)
     return out
 
 
@@ -105,6 +112,8 @@ class FitSedBatch:
         if scenario == "ec_blr_dt":
             self.plans["ec_blr"] = SedBatch("ec_blr", nu, ne_kind, gamma=gamma_to_integrate_ec, **kw)
             self.plans["ec_dt"] = SedBatch("ec_dt", nu, ne_kind, gamma=gamma_to_integrate_ec, **kw)
+            self.plans["bb_disk"] = SedBatch("bb_disk_norm", nu, ne_kind, device=device)
+            self.plans["bb_dt"] = SedBatch("bb_dt_norm", nu, ne_kind, device=device)
         self.n_nu = nu.size
         self.device = self.plans["synch"].device
         self.torch = self.plans["synch"].torch

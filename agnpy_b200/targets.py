@@ -4,8 +4,9 @@ path reads is kept (energy densities, black-body SEDs, printing and plotting sta
 reference)."""
 import numpy as np
 
-from . import constants as const
-from .units import strip, u
+from . import _core, _lib, constants as const
+from .grids import nu_to_integrate
+from .units import strip, u, wrap
 
 __all__ = ["CMB", "PointSourceBehindJet", "SSDisk", "SphericalShellBLR", "RingDustTorus",
            "Blob", "lines_dictionary"]
@@ -45,6 +46,35 @@ class SSDisk:
             self.R_in, self.R_out = R_in, R_out
             self.R_in_tilde = strip(R_in, "cm", "R_in") / R_g
             self.R_out_tilde = strip(R_out, "cm", "R_out") / R_g
+        # targets.py:247-248: m_dot = L_disk / (eta c^2)
+        self.m_dot = strip(L_disk, "erg s-1", "L_disk") / (eta * const.c**2) * u.Unit("g s-1")
+
+    @staticmethod
+    def _bb(variant, nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s, L_disk=None):
+        nu_hz = strip(nu, "Hz", "nu")
+        models = _lib.make_models(1)
+        tgt = [strip(M_BH, "g", "M_BH"), strip(m_dot, "g s-1", "m_dot"), strip(R_in, "cm", "R_in"),
+               strip(R_out, "cm", "R_out")]
+        if L_disk is not None:
+            tgt.append(strip(L_disk, "erg s-1", "L_disk"))
+        _core.model_row(models, 0, z=float(z), d_L=strip(d_L, "cm", "d_L"), mu_s=float(mu_s), tgt=tgt)
+        sed = _core.bb_sed_host(variant, models, np.ravel(nu_hz), nu_to_integrate, 100)
+        return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
+
+    @staticmethod
+    def evaluate_multi_T_bb_sed(nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s=1):
+        """multi-temperature black-body SED of the disk, targets.py:350-391"""
+        return SSDisk._bb(_lib.BB_DISK, nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s)
+
+    @staticmethod
+    def evaluate_multi_T_bb_norm_sed(nu, z, L_disk, M_BH, m_dot, R_in, R_out, d_L, mu_s=1):
+        """same, normalised to an integral luminosity L_disk, targets.py:393-415"""
+        return SSDisk._bb(_lib.BB_DISK_NORM, nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s, L_disk)
+
+    def sed_flux(self, nu, z, d_L, mu_s=1):
+        """targets.py:417-427; d_L must be given (the reference derives it from z)"""
+        return self.evaluate_multi_T_bb_norm_sed(nu, z, self.L_disk, self.M_BH, self.m_dot, self.R_in,
+                                                 self.R_out, d_L, mu_s)
 
 
 class SphericalShellBLR:
@@ -71,6 +101,32 @@ class RingDustTorus:
             self.R_dt = 3.5 * 1e18 * np.sqrt(L / 1e45) * np.power(T / 1e3, -2.6) * u.cm
         else:
             self.R_dt = R_dt
+
+    @staticmethod
+    def _bb(variant, nu, z, T_dt, R_dt, d_L, L_dt=None):
+        nu_hz = strip(nu, "Hz", "nu")
+        models = _lib.make_models(1)
+        tgt = [strip(T_dt, "K", "T_dt"), strip(R_dt, "cm", "R_dt")]
+        if L_dt is not None:
+            tgt.append(strip(L_dt, "erg s-1", "L_dt"))
+        _core.model_row(models, 0, z=float(z), d_L=strip(d_L, "cm", "d_L"), tgt=tgt)
+        sed = _core.bb_sed_host(variant, models, np.ravel(nu_hz), None, 2)
+        return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
+
+    @staticmethod
+    def evaluate_bb_sed(nu, z, T_dt, R_dt, d_L):
+        """black-body SED of the torus, targets.py:593-600"""
+        return RingDustTorus._bb(_lib.BB_DT, nu, z, T_dt, R_dt, d_L)
+
+    @staticmethod
+    def evaluate_bb_norm_sed(nu, z, L_dt, T_dt, R_dt, d_L):
+        """same, normalised to the torus luminosity, targets.py:602-610"""
+        return RingDustTorus._bb(_lib.BB_DT_NORM, nu, z, T_dt, R_dt, d_L, L_dt)
+
+    def sed_flux(self, nu, z, d_L):
+        """targets.py:612-618; d_L must be given (the reference derives it from z)"""
+        L_dt = self.xi_dt * strip(self.L_disk, "erg s-1", "L_disk") * u.Unit("erg s-1")
+        return self.evaluate_bb_norm_sed(nu, z, L_dt, self.T_dt, self.R_dt, d_L)
 
 
 class Blob:

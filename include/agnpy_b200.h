@@ -59,6 +59,13 @@ extern "C" {
 #define AGNPY_TAU_BLR 1     /* :284-353  tgt = {L_disk, xi_line, epsilon_line, R_line, r}        */
 #define AGNPY_TAU_DT 2      /* :474-532  tgt = {L_disk, xi_dt, epsilon_dt, R_dt, r}              */
 
+/* thermal black-body SEDs of the targets: agnpy/targets/targets.py (disk radii grid =
+ * linspace(R_in, R_out, n_R), 100 in the reference; mu_s is taken from the model) */
+#define AGNPY_BB_DISK 0      /* :350-391  tgt = {M_BH, m_dot, R_in, R_out}          */
+#define AGNPY_BB_DISK_NORM 1 /* :393-415  tgt = {M_BH, m_dot, R_in, R_out, L_disk}  */
+#define AGNPY_BB_DT 2        /* :593-600  tgt = {T_dt, R_dt}                        */
+#define AGNPY_BB_DT_NORM 3   /* :602-610  tgt = {T_dt, R_dt, L_dt}                  */
+
 /* error codes (0 = success); agnpy_b200_last_error() has the text */
 #define AGNPY_OK 0
 #define AGNPY_ERR_ARG 1
@@ -148,6 +155,19 @@ int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
                         const double* nu, int n_nu, const double* mu, int n_a,
                         const double* phi, int n_phi, const double* l_unit, int n_l,
                         double* tau);
+
+/* ---- thermal black-body SEDs (fit-wrapper components) -----------------------------------------
+ * replaces SSDisk.evaluate_multi_T_bb_sed / evaluate_multi_T_bb_norm_sed
+ *          agnpy/targets/targets.py:350-415
+ *      and RingDustTorus.evaluate_bb_sed / evaluate_bb_norm_sed   agnpy/targets/targets.py:593-610
+ * nu_norm[n_norm]: frequencies of the normalisation integral of AGNPY_BB_DISK_NORM
+ * (utils/math.py:7 `nu_to_integrate` in the reference); ignored otherwise (may be NULL). */
+int agnpy_b200_bb_sed(int variant, int n_models, const agnpy_model_t* models, const double* nu,
+                      int n_nu, const double* nu_norm, int n_norm, int n_R, double* sed,
+                      void* stream);
+int agnpy_b200_bb_sed_host(int variant, int n_models, const agnpy_model_t* models,
+                           const double* nu, int n_nu, const double* nu_norm, int n_norm, int n_R,
+                           double* sed);
 
 #ifdef __cplusplus
 }

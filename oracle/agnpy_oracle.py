@@ -752,3 +752,64 @@ def chunked_over_nu(fn, nu, chunk, *args, **kwargs):
     nu = np.asarray(nu, dtype=np.float64)
     out = [fn(nu[i:i + chunk], *args, **kwargs) for i in range(0, nu.size, chunk)]
     return np.concatenate(out)
+
+
+# --------------------------------------------------------------------------
+# thermal black-body SEDs added by the fit wrappers  (agnpy/targets/targets.py)
+# SURVEY.md 8(f) rank 1.  Planck's law is third-party arithmetic: astropy>=7
+# `astropy.modeling.physical_models.BlackBody.evaluate(nu, T, scale=1)`:
+#   B_nu = 2 h nu^3 / (c^2 expm1(h nu / (k_B T)))   [erg s-1 cm-2 Hz-1 sr-1]
+# --------------------------------------------------------------------------
+SIGMA_SB = 5.6703744191844314e-5
+
+
+def planck_nu(nu, T):
+    with np.errstate(all="ignore"):
+        log_boltz = H_PLANCK * nu / (K_B * T)
+        boltzm1 = np.expm1(log_boltz)
+        return 2.0 * H_PLANCK * nu**3 / (C_LIGHT**2 * boltzm1)
+
+
+def disk_T(R, M_BH, m_dot, R_in):
+    """targets.py:325-330"""
+    phi = 1 - np.sqrt(R_in / R)
+    val = (3 * G_NEWTON * M_BH * m_dot * phi) / (8 * np.pi * np.power(R, 3) * SIGMA_SB)
+    return np.power(val, 1 / 4)
+
+
+def disk_multi_T_bb_sed(nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s=1):
+    """targets.py:350-391"""
+    nu = np.asarray(nu, dtype=np.float64)
+    nu_prime = nu * (1 + z)
+    R = np.linspace(R_in, R_out, 100)
+    _R, _nu = broadcast_axes(R, nu_prime)
+    _T = disk_T(_R, M_BH, m_dot, R_in)
+    _I_nu = planck_nu(_nu, _T)
+    integrand = _R / np.power(d_L, 2) * _I_nu
+    F_nu = 2 * np.pi * trapz(integrand, R, axis=0)
+    return mu_s * (nu * F_nu)
+
+
+def disk_multi_T_bb_norm_sed(nu, z, L_disk, M_BH, m_dot, R_in, R_out, d_L, mu_s=1, nu_norm=None):
+    """targets.py:393-415"""
+    nu_norm = default_nu_seed() if nu_norm is None else nu_norm
+    F_nu_norm = disk_multi_T_bb_sed(nu_norm, z, M_BH, m_dot, R_in, R_out, d_L, mu_s) / nu_norm
+    A = 4 * np.pi * d_L**2
+    L = 2 * (trapz(F_nu_norm, nu_norm) * A)
+    norm = L_disk / L
+    return norm * disk_multi_T_bb_sed(nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s)
+
+
+def dt_bb_sed(nu, z, T_dt, R_dt, d_L):
+    """targets.py:593-600"""
+    nu = np.asarray(nu, dtype=np.float64)
+    nu_prime = nu * (1 + z)
+    prefactor = np.pi * np.power(R_dt / d_L, 2)
+    return prefactor * nu * planck_nu(nu_prime, T_dt)
+
+
+def dt_bb_norm_sed(nu, z, L_dt, T_dt, R_dt, d_L):
+    """targets.py:602-610"""
+    sed_dt = dt_bb_sed(nu, z, T_dt, R_dt, d_L)
+    L_tot = 4 * np.pi * R_dt**2 * SIGMA_SB * T_dt**4
+    return (L_dt / L_tot) * sed_dt

@@ -168,7 +168,9 @@ def test_fit_parameter_marshalling():
                       18.0, np.log10(2e46), 2.4e42, 1e26, 1e15, 1e17, 0.024, 1215.67, 1e17, 0.1, 1e3,
                       1.5e19]] * 2)
     m = fit.build_models(pars, 2.0957e28, "BrokenPowerLaw", "ec_blr_dt")
-    assert set(m) == {"synch", "ssc", "ec_blr", "ec_dt"}
+    assert set(m) == {"synch", "ssc", "ec_blr", "ec_dt", "bb_disk", "bb_dt"}
+    np.testing.assert_allclose(m["bb_disk"][0]["tgt"][:5], [2.4e42, 1e26, 1e15, 1e17, 2e46], rtol=1e-12)
+    np.testing.assert_allclose(m["bb_dt"][0]["tgt"][:3], [1e3, 1.5e19, 0.1 * 2e46], rtol=1e-12)
     b = m["ec_blr"][1]
     assert b["B"] == pytest.approx(10 ** -0.5) and b["mu_s"] == 0.9997 and m["synch"][0]["mu_s"] == 1.0
     assert b["R_b"] == pytest.approx(const.c * 86400.0 * 40 / 2)

@@ -146,3 +146,30 @@ def test_tau_disk_runs_and_is_sane():
     assert np.all(np.isfinite(tau)) and np.all(tau >= 0)
     assert tau[0] == 0.0
     assert 0.1 < tau.max() / ref.max() < 10
+
+
+@pytest.mark.parametrize("R_out", [1e2, 1e3, 1e4])
+@pytest.mark.parametrize("mu_s", [0.5, 0.8, 1.0])
+def test_disk_bb_luminosity(R_out, mu_s):
+    """targets/tests/test_targets.py:188-204: the normalised multi-T BB integrates back to
+    L_disk (10 %)"""
+    M_BH, L_disk, eta = 1.2e9 * orc.M_SUN, 1.512e46, 1 / 12
+    R_g = orc.G_NEWTON * M_BH / orc.C_LIGHT**2
+    m_dot = L_disk / (eta * orc.C_LIGHT**2)
+    z, d_L = 0.23, cases.lum_dist_cm(0.23)
+    nu = np.logspace(10, 20, 100)
+    sed = orc.disk_multi_T_bb_norm_sed(nu, z, L_disk, M_BH, m_dot, 6 * R_g, R_out * R_g, d_L, mu_s)
+    L = 2 * (4 * np.pi * d_L**2 * orc.trapz(sed / nu, nu))
+    assert np.isclose(L, L_disk, atol=0, rtol=0.1)
+
+
+@pytest.mark.parametrize("T_dt", [1e3, 2e3, 5e3])
+def test_dt_bb_luminosity(T_dt):
+    """targets/tests/test_targets.py:306-324: L < xi_dt L_disk, and close to it"""
+    L_disk, xi_dt = 1.512e46, 0.5
+    R_dt = orc.dt_sublimation_radius(L_disk, T_dt)
+    z, d_L = 0.23, cases.lum_dist_cm(0.23)
+    nu = np.logspace(10, 20, 100)
+    sed = orc.dt_bb_norm_sed(nu, z, xi_dt * L_disk, T_dt, R_dt, d_L)
+    L = 4 * np.pi * d_L**2 * orc.trapz(sed / nu, nu)
+    assert 0.8 * xi_dt * L_disk < L < xi_dt * L_disk
