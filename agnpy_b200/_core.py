@@ -57,13 +57,16 @@ def ec_sed_host(variant, models, ne_kind, nu, gamma, mu, n_mu, phi, ne_table=Non
 
 
 def tau_host(variant, models, nu, mu, n_a, phi, l_unit):
-    nu, phi, l_unit = f64(nu), f64(phi), f64(l_unit)
+    nu = f64(nu)
+    phi = None if phi is None else f64(phi)
+    l_unit = None if l_unit is None else f64(l_unit)
     mu = None if mu is None else f64(mu)
     n = len(models)
     tau = np.empty((n, nu.size))
     check(lib().agnpy_b200_tau_host(
-        variant, n, hptr(models), hptr(nu), nu.size, hptr(mu), int(n_a), hptr(phi), phi.size,
-        hptr(l_unit), l_unit.size, hptr(tau)), "agnpy_b200_tau_host")
+        variant, n, hptr(models), hptr(nu), nu.size, hptr(mu), int(n_a), hptr(phi),
+        0 if phi is None else phi.size, hptr(l_unit), 0 if l_unit is None else l_unit.size,
+        hptr(tau)), "agnpy_b200_tau_host")
     return tau
 
 

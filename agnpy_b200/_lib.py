@@ -17,6 +17,7 @@ NE_EXP_CUTOFF_POWERLAW, NE_EXP_CUTOFF_BROKEN_POWERLAW, NE_TABLE = 3, 4, 5
 INTEG_TRAPZ, INTEG_LOGLOG, INTEG_TRAPZ_PREFIX = 0, 1, 2
 EC_ISO_MONO, EC_PS_BEHIND_JET, EC_SS_DISK, EC_BLR, EC_DT = 0, 1, 2, 3, 4
 TAU_SS_DISK, TAU_BLR, TAU_DT = 0, 1, 2
+TAU_PS_BEHIND_BLOB, TAU_PS_BEHIND_BLOB_MU_S, TAU_BLR_MU_S, TAU_DT_MU_S = 3, 4, 5, 6
 BB_DISK, BB_DISK_NORM, BB_DT, BB_DT_NORM = 0, 1, 2, 3
 
 EXPORTS = [

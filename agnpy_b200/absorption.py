@@ -11,18 +11,24 @@ from .units import strip
 __all__ = ["Absorption"]
 
 
-def _tau_call(variant, nu, z, mu_s, tgt, mu, n_a, phi, l_size):
+def _tau_call(variant, nu, z, mu_s, tgt, mu, n_a, phi, l_size, off_axis=False):
     nu_hz = strip(nu, "Hz", "nu")
     models = _lib.make_models(1)
     _core.model_row(models, 0, z=float(z), mu_s=float(mu_s), tgt=tgt)
-    l_unit = np.logspace(0, 5, int(l_size))  # targets_absorption.py:237, 333, 520
-    tau = _core.tau_host(variant, models, np.ravel(nu_hz), mu, n_a, as_grid(phi, "phi"), l_unit)
+    if l_size is None:
+        l_unit = None
+    elif off_axis:  # path measured from the emission point, targets_absorption.py:153, 405, 576
+        l_unit = np.logspace(-5, 5, int(l_size))
+    else:           # path measured from the black hole, targets_absorption.py:237, 333, 520
+        l_unit = np.logspace(0, 5, int(l_size))
+    phi = None if phi is None else as_grid(phi, "phi")
+    tau = _core.tau_host(variant, models, np.ravel(nu_hz), mu, n_a, phi, l_unit)
     return tau[0].reshape(np.shape(nu_hz))
 
 
 class Absorption:
-    """targets_absorption.py:45-747 (on-axis targets; `mu_s != 1` and absorption on
-    synchrotron photons are not part of this build yet and raise)."""
+    """targets_absorption.py:45-747 (absorption on the blob's own synchrotron photons,
+    `tau_on_synchrotron`, is not part of this build yet and raises)."""
 
     def __init__(self, target, r=None, z=0, mu_s=1):
         self.target = target
@@ -74,6 +80,59 @@ class Absorption:
                strip(R_dt, "cm", "R_dt"), strip(r, "cm", "r")]
         return _tau_call(_lib.TAU_DT, nu, z, mu_s, tgt, None, 0, phi, l_size)
 
+    @staticmethod
+    def evaluate_tau_ps_behind_blob(nu, z, mu_s, epsilon_0, L_0, r):
+        """opacity on a point source behind the blob (closed form), targets_absorption.py:87-119"""
+        tgt = [float(epsilon_0), strip(L_0, "erg s-1", "L_0"), strip(r, "cm", "r")]
+        return _tau_call(_lib.TAU_PS_BEHIND_BLOB, nu, z, mu_s, tgt, None, 0, None, None)
+
+    @staticmethod
+    def evaluate_tau_ps_behind_blob_mu_s(nu, z, mu_s, epsilon_0, L_0, r, u_size=100):
+        """same, integrated along an off-axis path, targets_absorption.py:128-173"""
+        tgt = [float(epsilon_0), strip(L_0, "erg s-1", "L_0"), strip(r, "cm", "r")]
+        return _tau_call(_lib.TAU_PS_BEHIND_BLOB_MU_S, nu, z, mu_s, tgt, None, 0, None, u_size,
+                         off_axis=True)
+
+    @staticmethod
+    def evaluate_tau_blr_mu_s(nu, z, mu_s, L_disk, xi_line, epsilon_line, R_line, r, u_size=100,
+                              mu=mu_to_integrate, phi=phi_to_integrate):
+        """opacity on a spherical-shell BLR for any viewing angle, targets_absorption.py:355-436"""
+        mu = as_grid(mu, "mu")
+        tgt = [strip(L_disk, "erg s-1", "L_disk"), float(xi_line), float(epsilon_line),
+               strip(R_line, "cm", "R_line"), strip(r, "cm", "r")]
+        return _tau_call(_lib.TAU_BLR_MU_S, nu, z, mu_s, tgt, mu, mu.size, phi, u_size, off_axis=True)
+
+    @staticmethod
+    def evaluate_tau_dt_mu_s(nu, z, mu_s, L_disk, xi_dt, epsilon_dt, R_dt, r, u_size=100,
+                             phi_re=phi_to_integrate):
+        """opacity on a ring dust torus for any viewing angle, targets_absorption.py:534-597"""
+        tgt = [strip(L_disk, "erg s-1", "L_disk"), float(xi_dt), float(epsilon_dt),
+               strip(R_dt, "cm", "R_dt"), strip(r, "cm", "r")]
+        return _tau_call(_lib.TAU_DT_MU_S, nu, z, mu_s, tgt, None, 0, phi_re, u_size, off_axis=True)
+
+    def tau_ps_behind_blob(self, nu):
+        """targets_absorption.py:121-126"""
+        t = self.target
+        return self.evaluate_tau_ps_behind_blob(nu, self.z, self.mu_s, t.epsilon_0, t.L_0, self.r)
+
+    def tau_ps_behind_blob_mu_s(self, nu):
+        """targets_absorption.py:175-180"""
+        t = self.target
+        return self.evaluate_tau_ps_behind_blob_mu_s(nu, self.z, self.mu_s, t.epsilon_0, t.L_0, self.r)
+
+    def tau_blr_mu_s(self, nu):
+        """targets_absorption.py:456-472"""
+        t = self.target
+        return self.evaluate_tau_blr_mu_s(nu, self.z, self.mu_s, t.L_disk, t.xi_line, t.epsilon_line,
+                                          t.R_line, self.r, u_size=2 * self.l_size, mu=self.mu,
+                                          phi=self.phi)
+
+    def tau_dt_mu_s(self, nu):
+        """targets_absorption.py:616-630"""
+        t = self.target
+        return self.evaluate_tau_dt_mu_s(nu, self.z, self.mu_s, t.L_disk, t.xi_dt, t.epsilon_dt,
+                                         t.R_dt, self.r, u_size=2 * self.l_size, phi_re=self.phi)
+
     def tau_ss_disk(self, nu):
         """targets_absorption.py:266-282"""
         t = self.target
@@ -97,12 +156,17 @@ class Absorption:
     def tau(self, nu):
         """targets_absorption.py:696-730"""
         kind = _target_kind(self.target)
-        if self.mu_s != 1:
-            raise NotImplementedError("off-axis opacities (mu_s != 1) are not built yet")
-        if kind == "PointSourceBehindJet":  # identically zero on axis (:714)
-            return np.zeros(np.shape(strip(nu, "Hz", "nu")))
-        fn = {"SSDisk": self.tau_ss_disk, "SphericalShellBLR": self.tau_blr,
-              "RingDustTorus": self.tau_dt}.get(kind)
+        if kind == "Blob":
+            raise NotImplementedError("absorption on synchrotron photons is not built yet")
+        if self.mu_s == 1:
+            table = {"PointSourceBehindJet": self.tau_ps_behind_blob, "SSDisk": self.tau_ss_disk,
+                     "SphericalShellBLR": self.tau_blr, "RingDustTorus": self.tau_dt}
+        else:  # the reference has no off-axis disk opacity either (:724-726)
+            table = {"PointSourceBehindJet": self.tau_ps_behind_blob_mu_s,
+                     "SphericalShellBLR": self.tau_blr_mu_s, "RingDustTorus": self.tau_dt_mu_s}
+            if kind == "SSDisk":
+                raise NotImplementedError("off-axis opacity on the disk does not exist in agnpy")
+        fn = table.get(kind)
         if fn is None:
             raise TypeError(f"unsupported target {type(self.target).__name__!r}")
         return fn(nu)

@@ -23,7 +23,11 @@ _NE_KINDS = {"PowerLaw": _lib.NE_POWERLAW, "BrokenPowerLaw": _lib.NE_BROKEN_POWE
              "ExpCutoffBrokenPowerLaw": _lib.NE_EXP_CUTOFF_BROKEN_POWERLAW}
 _EC = {"ec_iso_mono": _lib.EC_ISO_MONO, "ec_ps_behind_jet": _lib.EC_PS_BEHIND_JET,
        "ec_ss_disk": _lib.EC_SS_DISK, "ec_blr": _lib.EC_BLR, "ec_dt": _lib.EC_DT}
-_TAU = {"tau_ss_disk": _lib.TAU_SS_DISK, "tau_blr": _lib.TAU_BLR, "tau_dt": _lib.TAU_DT}
+_TAU = {"tau_ss_disk": _lib.TAU_SS_DISK, "tau_blr": _lib.TAU_BLR, "tau_dt": _lib.TAU_DT,
+        "tau_ps_behind_blob": _lib.TAU_PS_BEHIND_BLOB,
+        "tau_ps_behind_blob_mu_s": _lib.TAU_PS_BEHIND_BLOB_MU_S,
+        "tau_blr_mu_s": _lib.TAU_BLR_MU_S, "tau_dt_mu_s": _lib.TAU_DT_MU_S}
+_TAU_OFF_AXIS = ("tau_ps_behind_blob_mu_s", "tau_blr_mu_s", "tau_dt_mu_s")
 _BB = {"bb_disk": _lib.BB_DISK, "bb_disk_norm": _lib.BB_DISK_NORM, "bb_dt": _lib.BB_DT,
        "bb_dt_norm": _lib.BB_DT_NORM}
 PROCESSES = ("synch", "ssc") + tuple(_EC) + tuple(_TAU) + tuple(_BB)
@@ -132,7 +136,8 @@ class SedBatch:
         self.mu = dev(grids.mu_to_integrate if mu is None else grids.as_grid(mu, "mu"))
         self.phi = dev(grids.phi_to_integrate if phi is None else grids.as_grid(phi, "phi"))
         self.nu_seed = dev(grids.nu_to_integrate if nu_seed is None else nu_seed)
-        self.l_unit = dev(np.logspace(0, 5, int(l_size)))
+        self.l_unit = dev(np.logspace(-5, 5, int(l_size)) if process in _TAU_OFF_AXIS
+                          else np.logspace(0, 5, int(l_size)))
         self._pinned_in = self._pinned_out = self._d_models = self._d_out = None
 
     # -- buffers sized for the largest batch seen so far
@@ -174,7 +179,7 @@ class SedBatch:
                                      d_out.data_ptr(), st)
         else:
             v = _TAU[p]
-            mu_ptr = self.mu.data_ptr() if v == _lib.TAU_BLR else None
+            mu_ptr = self.mu.data_ptr() if v in (_lib.TAU_BLR, _lib.TAU_BLR_MU_S) else None
             n_a = self.mu_size if v == _lib.TAU_SS_DISK else self.mu.numel()
             rc = L.agnpy_b200_tau(v, n, d_models.data_ptr(), self.nu.data_ptr(), self.n_nu, mu_ptr,
                                   n_a, self.phi.data_ptr(), self.phi.numel(),

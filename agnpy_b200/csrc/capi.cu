@@ -168,10 +168,14 @@ int agnpy_b200_tau(int variant, int n_models, const agnpy_model_t* models, const
                    int n_nu, const double* mu, int n_a, const double* phi, int n_phi,
                    const double* l_unit, int n_l, double* tau, void* stream_) {
     if (int rc = need_device()) return rc;
-    if (variant < AGNPY_TAU_SS_DISK || variant > AGNPY_TAU_DT) return fail(AGNPY_ERR_ARG, "tau: bad variant");
-    if (n_models < 1 || n_nu < 1 || n_phi < 2 || n_l < 2 || !models || !nu || !phi || !l_unit || !tau)
+    if (variant < AGNPY_TAU_SS_DISK || variant > AGNPY_TAU_DT_MU_S) return fail(AGNPY_ERR_ARG, "tau: bad variant");
+    const bool is_ps = variant == AGNPY_TAU_PS_BEHIND_BLOB || variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S;
+    if (n_models < 1 || n_nu < 1 || !models || !nu || !tau)
         return fail(AGNPY_ERR_ARG, "tau: bad sizes or null pointer");
-    if (variant == AGNPY_TAU_BLR && (!mu || n_a < 2)) return fail(AGNPY_ERR_ARG, "tau: mu grid required");
+    if (!is_ps && (n_phi < 2 || !phi)) return fail(AGNPY_ERR_ARG, "tau: phi grid required");
+    if (variant != AGNPY_TAU_PS_BEHIND_BLOB && (n_l < 2 || !l_unit)) return fail(AGNPY_ERR_ARG, "tau: path grid required");
+    if ((variant == AGNPY_TAU_BLR || variant == AGNPY_TAU_BLR_MU_S) && (!mu || n_a < 2))
+        return fail(AGNPY_ERR_ARG, "tau: mu grid required");
     if (variant == AGNPY_TAU_SS_DISK && n_a < 2) return fail(AGNPY_ERR_ARG, "tau: R_tilde_size < 2");
     if ((n_nu + 3) / 4 > 65535) return fail(AGNPY_ERR_ARG, "tau: n_nu too large");
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -396,13 +400,13 @@ int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
                         const double* phi, int n_phi, const double* l_unit, int n_l,
                         double* tau) {
     if (int rc = need_device()) return rc;
-    if (n_models < 1 || n_nu < 1 || n_phi < 2 || n_l < 2 || !models || !nu || !phi || !l_unit || !tau)
+    if (n_models < 1 || n_nu < 1 || !models || !nu || !tau)
         return fail(AGNPY_ERR_ARG, "tau_host: bad sizes or null pointer");
     size_t out_n = (size_t)n_models * n_nu;
     HostIO io;
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
-    int i_mu = io.in(mu, 8 * (size_t)(n_a > 0 ? n_a : 0)), i_ph = io.in(phi, 8 * (size_t)n_phi);
-    int i_l = io.in(l_unit, 8 * (size_t)n_l);
+    int i_mu = io.in(mu, 8 * (size_t)(n_a > 0 ? n_a : 0)), i_ph = io.in(phi, 8 * (size_t)(n_phi > 0 ? n_phi : 0));
+    int i_l = io.in(l_unit, 8 * (size_t)(n_l > 0 ? n_l : 0));
     int o_tau = io.out(tau, 8 * out_n);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;

@@ -42,12 +42,61 @@ __device__ __forceinline__ double disk_eps(double L_disk, double M_BH, double et
     return 2.7 * 1e-4 * xi * pow(R_tilde, -3.0 / 4.0);
 }
 
+// ---- off-axis geometry, utils/geometry.py:58-183, in the reference's operation order ----------
+__device__ __forceinline__ double x_ring_mu_s(double R, double r, double phi_re, double u, double mu_s) {
+    double sin_s = sqrt(1.0 - mu_s * mu_s);
+    double x2 = u * u + R * R + r * r - 2.0 * u * R * sin_s * cos(phi_re) + 2.0 * r * u * mu_s;
+    return sqrt(x2);
+}
+__device__ __forceinline__ double x_shell_mu_s(double R, double r, double phi_re, double mu_re, double u,
+                                               double mu_s) {
+    double sin_re = sqrt(1.0 - mu_re * mu_re);
+    double sin_s = sqrt(1.0 - mu_s * mu_s);
+    double x2 = R * R + u * u + r * r - 2.0 * R * u * sin_re * cos(phi_re) * sin_s -
+                2.0 * R * mu_re * (r + u * mu_s) + 2.0 * r * u * mu_s;
+    return sqrt(x2);
+}
+
+// targets_absorption.py:405-415: the off-axis BLR path grid uu = l_unit * r, nudged off the
+// shell crossing (np.isclose, rtol 1e-4) and re-sorted when anything was nudged.
+// path[m][i], one block per model, rank sort (n_l is ~100).
+__global__ void __launch_bounds__(128) tau_blr_path_kernel(
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ l_unit, int n_l,
+    double* __restrict__ path) {
+    extern __shared__ double s_u[];
+    __shared__ int s_any;
+    const int m = blockIdx.x;
+    const agnpy_model_t& M = models[m];
+    const double R_line = M.tgt[3], r = M.tgt[4], mu_s = M.mu_s;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_l; i += blockDim.x) {
+        double u = l_unit[i] * r;
+        double x_cross = sqrt(r * r + u * u + 2.0 * u * r * mu_s);
+        if (fabs(x_cross - R_line) <= 1e-8 + 1.0e-4 * fabs(R_line)) {
+            u += 1.0e-4 * R_line;
+            s_any = 1;
+        }
+        s_u[i] = u;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_l; i += blockDim.x) {
+        double u = s_u[i];
+        int rank = i;
+        if (s_any) {  // stable rank = position after np.sort
+            rank = 0;
+            for (int j = 0; j < n_l; ++j) rank += (s_u[j] < u) || (s_u[j] == u && j < i);
+        }
+        path[(size_t)m * n_l + rank] = u;
+    }
+}
+
 // table[m][0][t] = p_t (target energy)   table[m][1][t] = (1 - cos psi)/2
 // table[m][2][t] = 1/(p_t (1-cos psi)/2)  table[m][3][t] = W_t
 __global__ void __launch_bounds__(128) tau_table_kernel(
     int variant, const agnpy_model_t* __restrict__ models, const double* __restrict__ mu, int n_a,
     const double* __restrict__ phi, int n_phi, const double* __restrict__ l_unit, int n_l,
-    int n_t, double* __restrict__ table) {
+    int n_t, const double* __restrict__ path, double* __restrict__ table) {
     int m = blockIdx.y;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_t) return;
@@ -56,9 +105,52 @@ __global__ void __launch_bounds__(128) tau_table_kernel(
     int il = t % n_l;
     int iphi = (t / n_l) % n_phi;
     int ia = t / (n_l * n_phi);
-    double wphi = trapz_weight(phi, iphi, n_phi);
+    double wphi = (variant == AGNPY_TAU_PS_BEHIND_BLOB || variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S)
+                      ? 1.0 : trapz_weight(phi, iphi, n_phi);
     double p, omc, W;
-    if (variant == AGNPY_TAU_DT) {  // targets_absorption.py:520-530
+    if (variant == AGNPY_TAU_PS_BEHIND_BLOB) {  // targets_absorption.py:114-118 (closed form)
+        p = g[0];
+        omc = 1.0 - M.mu_s;
+        W = omc / g[2];
+    } else if (variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S) {  // :155-171
+        double r = g[2], mu_s = M.mu_s;
+        double u = l_unit[il] * r;
+        double ulo = l_unit[il > 0 ? il - 1 : 0] * r, uhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r;
+        double wl = n_l < 2 ? 0.0 : (uhi - ulo) * 0.5;
+        double x = sqrt(r * r + u * u + 2.0 * u * r * mu_s);
+        double mu_l = (r + u * mu_s) / x;
+        omc = 1.0 - cos_psi_t(mu_s, mu_l, 0.0);
+        p = g[0];
+        W = wl * (omc / (x * x));
+    } else if (variant == AGNPY_TAU_DT_MU_S) {  // :578-594, utils/geometry.py:58-118
+        double R_dt = g[3], r = g[4], mu_s = M.mu_s;
+        double u = l_unit[il] * r;
+        double ulo = l_unit[il > 0 ? il - 1 : 0] * r, uhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r;
+        double wl = n_l < 2 ? 0.0 : (uhi - ulo) * 0.5;
+        double phi_re = phi[iphi];
+        double sin_s = sqrt(1.0 - mu_s * mu_s);
+        double x = x_ring_mu_s(R_dt, r, phi_re, u, mu_s);
+        double dx = u * sin_s - R_dt * cos(phi_re);
+        double dy = 0.0 - R_dt * sin(phi_re);
+        double dz = r + u * mu_s;
+        omc = 1.0 - cos_psi_t(mu_s, dz / x, atan2(dy, dx));
+        p = g[2];
+        W = wphi * wl * (omc / (x * x));
+    } else if (variant == AGNPY_TAU_BLR_MU_S) {  // :416-433, utils/geometry.py:121-183
+        double R_line = g[3], r = g[4], mu_s = M.mu_s;
+        const double* uu = path + (size_t)m * n_l;
+        double u = uu[il];
+        double wl = n_l < 2 ? 0.0 : (uu[il < n_l - 1 ? il + 1 : n_l - 1] - uu[il > 0 ? il - 1 : 0]) * 0.5;
+        double mu_re = mu[ia], phi_re = phi[iphi];
+        double sin_s = sqrt(1.0 - mu_s * mu_s), sin_re = sqrt(1.0 - mu_re * mu_re);
+        double x = x_shell_mu_s(R_line, r, phi_re, mu_re, u, mu_s);
+        double dx = u * sin_s - R_line * sin_re * cos(phi_re);
+        double dy = -R_line * sin_re * sin(phi_re);
+        double dz = r + u * mu_s - R_line * mu_re;
+        omc = 1.0 - cos_psi_t(mu_s, dz / x, atan2(dy, dx));
+        p = g[2];
+        W = trapz_weight(mu, ia, n_a) * wphi * wl * (omc / (x * x));
+    } else if (variant == AGNPY_TAU_DT) {  // targets_absorption.py:520-530
         double R_dt = g[3], r = g[4];
         double l = l_unit[il] * r;
         double llo = l_unit[il > 0 ? il - 1 : 0] * r, lhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r;
@@ -177,10 +269,12 @@ __global__ void __launch_bounds__(128) tau_finish_kernel(
     integral = integral * (3.0 / 16.0 * kSigmaT);
     double c3 = kC * kC * kC;
     double pref;
-    if (variant == AGNPY_TAU_BLR)  // :350-352
+    if (variant == AGNPY_TAU_BLR || variant == AGNPY_TAU_BLR_MU_S)  // :350-352, 433-435
         pref = (g[0] * g[1]) / ((4.0 * kPi) * (4.0 * kPi) * g[2] * kMe * c3);
-    else if (variant == AGNPY_TAU_DT)  // :531
+    else if (variant == AGNPY_TAU_DT || variant == AGNPY_TAU_DT_MU_S)  // :531, 596
         pref = (g[0] * g[1]) / (8.0 * (kPi * kPi) * g[2] * kMe * c3);
+    else if (variant == AGNPY_TAU_PS_BEHIND_BLOB || variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S)  // :118, 172
+        pref = g[1] / (4.0 * kPi * g[0] * kMe * c3);
     else {  // :263
         double R_g = kG * g[0] / (kC * kC);
         pref = 3.0 * g[1] / ((4.0 * kPi) * (4.0 * kPi) * g[2] * kMe * c3 * R_g);
@@ -189,13 +283,16 @@ __global__ void __launch_bounds__(128) tau_finish_kernel(
 }
 
 static int tau_n_t(int variant, int n_a, int n_phi, int n_l) {
-    return (variant == AGNPY_TAU_DT ? 1 : n_a) * n_phi * n_l;
+    if (variant == AGNPY_TAU_PS_BEHIND_BLOB) return 1;
+    if (variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S) return n_l;
+    if (variant == AGNPY_TAU_DT || variant == AGNPY_TAU_DT_MU_S) return n_phi * n_l;
+    return n_a * n_phi * n_l;
 }
 
 size_t tau_workspace_bytes(int variant, int n_models, int n_nu, int n_a, int n_phi, int n_l) {
     size_t n_t = tau_n_t(variant, n_a, n_phi, n_l);
     size_t S = (n_t + kTauSlice - 1) / kTauSlice;
-    return (4 * n_t + (size_t)n_nu * S) * sizeof(double) * (size_t)n_models;
+    return (4 * n_t + (size_t)n_nu * S + (size_t)n_l) * sizeof(double) * (size_t)n_models;
 }
 
 int run_tau(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
@@ -205,10 +302,18 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
     int S = (n_t + kTauSlice - 1) / kTauSlice;
     double* table = ws;
     double* part = table + (size_t)n_models * 4 * n_t;
+    double* path = part + (size_t)n_models * n_nu * S;
+    int nl_eff = n_l, nphi_eff = n_phi;
+    if (variant == AGNPY_TAU_PS_BEHIND_BLOB) { nl_eff = 1; nphi_eff = 1; }
+    if (variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S) nphi_eff = 1;
+    if (variant == AGNPY_TAU_BLR_MU_S) {
+        tau_blr_path_kernel<<<n_models, 128, (size_t)n_l * sizeof(double), stream>>>(models, l_unit, n_l, path);
+        note_launch();
+    }
     {
         dim3 grid((n_t + 127) / 128, n_models);
-        tau_table_kernel<<<grid, 128, 0, stream>>>(variant, models, mu, n_a, phi, n_phi, l_unit,
-                                                   n_l, n_t, table);
+        tau_table_kernel<<<grid, 128, 0, stream>>>(variant, models, mu, n_a, phi, nphi_eff, l_unit,
+                                                   nl_eff, n_t, path, table);
         note_launch();
     }
     {

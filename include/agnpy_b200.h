@@ -58,6 +58,12 @@ extern "C" {
 #define AGNPY_TAU_SS_DISK 0 /* :182-264  tgt = {M_BH, L_disk, eta, R_in, R_out, r}               */
 #define AGNPY_TAU_BLR 1     /* :284-353  tgt = {L_disk, xi_line, epsilon_line, R_line, r}        */
 #define AGNPY_TAU_DT 2      /* :474-532  tgt = {L_disk, xi_dt, epsilon_dt, R_dt, r}              */
+/* off-axis (mu_s != 1) and point-source variants; l_unit = numpy.logspace(-5, 5, u_size) for the
+ * three *_MU_S variants (the path is measured from the emission point, :153, 405, 576) */
+#define AGNPY_TAU_PS_BEHIND_BLOB 3      /* :87-119   tgt = {epsilon_0, L_0, r}  (closed form)    */
+#define AGNPY_TAU_PS_BEHIND_BLOB_MU_S 4 /* :128-173  tgt = {epsilon_0, L_0, r}                   */
+#define AGNPY_TAU_BLR_MU_S 5            /* :355-436  tgt as AGNPY_TAU_BLR                        */
+#define AGNPY_TAU_DT_MU_S 6             /* :534-597  tgt as AGNPY_TAU_DT                         */
 
 /* thermal black-body SEDs of the targets: agnpy/targets/targets.py (disk radii grid =
  * linspace(R_in, R_out, n_R), 100 in the reference; mu_s is taken from the model) */

@@ -813,3 +813,122 @@ def dt_bb_norm_sed(nu, z, L_dt, T_dt, R_dt, d_L):
     sed_dt = dt_bb_sed(nu, z, T_dt, R_dt, d_L)
     L_tot = 4 * np.pi * R_dt**2 * SIGMA_SB * T_dt**4
     return (L_dt / L_tot) * sed_dt
+
+
+# --------------------------------------------------------------------------
+# off-axis geometry and opacities
+# agnpy/utils/geometry.py:58-183, agnpy/absorption/targets_absorption.py:87-173, 355-436, 534-597
+# --------------------------------------------------------------------------
+def x_re_ring_mu_s(R_re, r, phi_re, u, mu_s):
+    """utils/geometry.py:58-86"""
+    sin_theta_s = np.sqrt(1 - mu_s * mu_s)
+    x2 = (u * u + R_re * R_re + r * r - 2 * u * R_re * sin_theta_s * np.cos(phi_re)
+          + 2 * r * u * mu_s)
+    return np.sqrt(x2)
+
+
+def phi_mu_re_ring(R_re, r, phi_re, u, mu_s):
+    """utils/geometry.py:89-118"""
+    sin_theta_s = np.sqrt(1 - mu_s * mu_s)
+    dx = u * sin_theta_s - R_re * np.cos(phi_re)
+    dy = 0 - R_re * np.sin(phi_re)
+    dz = r + u * mu_s
+    phi = np.arctan2(dy, dx)
+    x = x_re_ring_mu_s(R_re, r, phi_re, u, mu_s)
+    return phi, dz / x
+
+
+def x_re_shell_mu_s(R_re, r, phi_re, mu_re, u, mu_s):
+    """utils/geometry.py:121-153"""
+    sin_re = np.sqrt(1 - mu_re * mu_re)
+    sin_s = np.sqrt(1 - mu_s * mu_s)
+    x2 = (R_re * R_re + u * u + r * r - 2 * R_re * u * sin_re * np.cos(phi_re) * sin_s
+          - 2 * R_re * mu_re * (r + u * mu_s) + 2 * r * u * mu_s)
+    return np.sqrt(x2)
+
+
+def phi_mu_re_shell(R_re, r, phi_re, mu_re, u, mu_s):
+    """utils/geometry.py:156-183"""
+    sin_theta_s = np.sqrt(1 - mu_s * mu_s)
+    sin_re = np.sqrt(1 - mu_re * mu_re)
+    dx = u * sin_theta_s - R_re * sin_re * np.cos(phi_re)
+    dy = -R_re * sin_re * np.sin(phi_re)
+    dz = r + u * mu_s - R_re * mu_re
+    phi = np.arctan2(dy, dx)
+    x = x_re_shell_mu_s(R_re, r, phi_re, mu_re, u, mu_s)
+    return phi, dz / x
+
+
+def tau_ps_behind_blob(nu, z, mu_s, epsilon_0, L_0, r):
+    """targets_absorption.py:87-119"""
+    epsilon_1 = nu_to_epsilon_prime(nu, z)
+    s = epsilon_0 * epsilon_1 * (1 - mu_s) / 2
+    integral = (1 - mu_s) * sigma_gg(s) / r
+    prefactor = L_0 / (4 * np.pi * epsilon_0 * M_E * C_LIGHT**3)
+    return prefactor * integral
+
+
+def tau_ps_behind_blob_mu_s(nu, z, mu_s, epsilon_0, L_0, r, u_size=100):
+    """targets_absorption.py:128-173"""
+    epsilon_1 = nu_to_epsilon_prime(nu, z)
+    uu = np.logspace(-5, 5, u_size) * r
+    _u, _eps1 = broadcast_axes(uu, epsilon_1)
+    with np.errstate(all="ignore"):
+        x = np.sqrt(r * r + _u * _u + 2 * _u * r * mu_s)
+        _mu = (r + _u * mu_s) / x
+        _cos_psi = cos_psi(mu_s, _mu, 0)
+        s = _eps1 * epsilon_0 * (1 - _cos_psi) / 2
+        integrand = (1 - _cos_psi) / x**2 * sigma_gg(s)
+    integral = trapz(integrand, uu, axis=0)
+    prefactor = L_0 / (4 * np.pi * epsilon_0 * M_E * C_LIGHT**3)
+    return prefactor * integral
+
+
+def tau_blr_mu_s_path(R_line, r, mu_s, u_size=100):
+    """targets_absorption.py:405-415: path grid, nudged off the shell crossing and re-sorted"""
+    uu = np.logspace(-5, 5, u_size) * r
+    x_cross = np.sqrt(r**2 + uu**2 + 2 * uu * r * mu_s)
+    idx = np.isclose(x_cross, R_line, rtol=MIN_REL_DISTANCE)
+    if idx.any():
+        uu[idx] += MIN_REL_DISTANCE * R_line
+        uu = np.sort(uu)
+    return uu
+
+
+def tau_blr_mu_s(nu, z, mu_s, L_disk, xi_line, epsilon_line, R_line, r, u_size=100, mu=None,
+                 phi=None):
+    """targets_absorption.py:355-436"""
+    mu = default_mu() if mu is None else mu
+    phi = default_phi() if phi is None else phi
+    epsilon_1 = nu_to_epsilon_prime(nu, z)
+    uu = tau_blr_mu_s_path(R_line, r, mu_s, u_size)
+    _mu_re, _phi_re, _u, _eps1 = broadcast_axes(mu, phi, uu, epsilon_1)
+    with np.errstate(all="ignore"):
+        x = x_re_shell_mu_s(R_line, r, _phi_re, _mu_re, _u, mu_s)
+        _phi, _mu_star = phi_mu_re_shell(R_line, r, _phi_re, _mu_re, _u, mu_s)
+        _cos_psi = cos_psi(mu_s, _mu_star, _phi)
+        s = _eps1 * epsilon_line * (1 - _cos_psi) / 2
+        integrand = (1 - _cos_psi) / x**2 * sigma_gg(s)
+    i_mu = trapz(integrand, mu, axis=0)
+    i_phi = trapz(i_mu, phi, axis=0)
+    integral = trapz(i_phi, uu, axis=0)
+    prefactor = (L_disk * xi_line) / ((4 * np.pi) ** 2 * epsilon_line * M_E * C_LIGHT**3)
+    return prefactor * integral
+
+
+def tau_dt_mu_s(nu, z, mu_s, L_disk, xi_dt, epsilon_dt, R_dt, r, u_size=100, phi_re=None):
+    """targets_absorption.py:534-597"""
+    phi_re = default_phi() if phi_re is None else phi_re
+    epsilon_1 = nu_to_epsilon_prime(nu, z)
+    uu = np.logspace(-5, 5, u_size) * r
+    _phi_re, _u, _eps1 = broadcast_axes(phi_re, uu, epsilon_1)
+    with np.errstate(all="ignore"):
+        x = x_re_ring_mu_s(R_dt, r, _phi_re, _u, mu_s)
+        _phi, _mu = phi_mu_re_ring(R_dt, r, _phi_re, _u, mu_s)
+        _cos_psi = cos_psi(mu_s, _mu, _phi)
+        s = _eps1 * epsilon_dt * (1 - _cos_psi) / 2
+        integrand = (1 - _cos_psi) / x**2 * sigma_gg(s)
+    i_phi = trapz(integrand, phi_re, axis=0)
+    integral = trapz(i_phi, uu, axis=0)
+    prefactor = (L_disk * xi_dt) / (8 * np.pi**2 * epsilon_dt * M_E * C_LIGHT**3)
+    return prefactor * integral

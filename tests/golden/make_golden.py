@@ -74,6 +74,18 @@ def make_kernel_fixture():
         out["x_re_shell"] = np.stack([ref_geom.x_re_shell(mu, R_re, ri) for ri in r])
         out["mu_star_shell"] = np.stack([ref_geom.mu_star_shell(mu, R_re, ri) for ri in r])
         out["x_re_ring"] = ref_geom.x_re_ring(1.5652e19, r)
+        # ---- off-axis geometry (utils/geometry.py:58-183) -------------------
+        phi_re = np.linspace(0, 2 * np.pi, 17)[None, :, None]
+        mu_re = np.linspace(-1, 1, 13)[:, None, None]
+        uu = (np.logspace(-5, 5, 21) * 3e17)[None, None, :]
+        out["off_phi_re"], out["off_mu_re"], out["off_u"] = phi_re.ravel(), mu_re.ravel(), uu.ravel()
+        for tag, mus in (("a", 0.9999), ("b", 0.5), ("c", 0.0)):
+            out[f"x_ring_{tag}"] = ref_geom.x_re_ring_mu_s(1e18, 3e17, phi_re, uu, mus)
+            ph, mu_ = ref_geom.phi_mu_re_ring(1e18, 3e17, phi_re, uu, mus)
+            out[f"phi_ring_{tag}"], out[f"mu_ring_{tag}"] = ph, mu_
+            out[f"x_shell_{tag}"] = ref_geom.x_re_shell_mu_s(1e17, 3e17, phi_re, mu_re, uu, mus)
+            ph, mu_ = ref_geom.phi_mu_re_shell(1e17, 3e17, phi_re, mu_re, uu, mus)
+            out[f"phi_shell_{tag}"], out[f"mu_shell_{tag}"] = ph, mu_
         # ---- Compton kernels -------------------------------------------
         gamma = np.logspace(1, 9, 61)
         eps = np.logspace(-12, 0, 25)

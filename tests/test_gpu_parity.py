@@ -329,3 +329,74 @@ def test_tau_ss_disk(r):
         t["nu"] * u.Hz, t["z"], 1.0, cases.M_BH * u.g, 2e46 * u.Unit("erg s-1"), 1 / 12,
         6 * cases.R_G * u.cm, 200 * cases.R_G * u.cm, r * u.cm)
     assert_parity(got, ref, what=f"tau disk r={r:g}")
+
+
+# ---------------------------------------------------------------------------------------------
+# off-axis and point-source opacities
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mu_s", [0.9999, 0.99, 0.5, 0.0])
+@pytest.mark.parametrize("r", [1.1e16, 1e17, 1.1e18])
+def test_tau_blr_mu_s(mu_s, r):
+    nu = np.logspace(24, 30, 24)
+    mu, phi = np.linspace(-1, 1, 40), np.linspace(0, 2 * np.pi, 24)
+    ref = orc.tau_blr_mu_s(nu, 0.859, mu_s, 2e46, 0.024, cases.EPS_LINE, 1e17, r, u_size=60, mu=mu, phi=phi)
+    got = ab.Absorption.evaluate_tau_blr_mu_s(nu * u.Hz, 0.859, mu_s, 2e46 * u.Unit("erg s-1"), 0.024,
+                                              cases.EPS_LINE, 1e17 * u.cm, r * u.cm, u_size=60, mu=mu, phi=phi)
+    assert_parity(got, ref, what=f"tau blr mu_s={mu_s} r={r:g}")
+
+
+def test_tau_blr_mu_s_crossing_nudge_and_sort():
+    """r == R_line: every small-u path point sits on the shell, is nudged and overtakes its
+    un-nudged neighbours, so the grid is re-sorted (targets_absorption.py:407-415)"""
+    nu = np.logspace(24, 29, 16)
+    mu, phi = np.linspace(-1, 1, 30), np.linspace(0, 2 * np.pi, 20)
+    R_line = 1.1e17
+    path = orc.tau_blr_mu_s_path(R_line, R_line, 0.99, 100)
+    assert np.any(np.diff(np.logspace(-5, 5, 100) * R_line + 0) != np.diff(path))  # something moved
+    ref = orc.tau_blr_mu_s(nu, 0.0, 0.99, 2e46, 0.024, cases.EPS_LINE, R_line, R_line, u_size=100, mu=mu, phi=phi)
+    got = ab.Absorption.evaluate_tau_blr_mu_s(nu * u.Hz, 0.0, 0.99, 2e46 * u.Unit("erg s-1"), 0.024,
+                                              cases.EPS_LINE, R_line * u.cm, R_line * u.cm, u_size=100,
+                                              mu=mu, phi=phi)
+    assert_parity(got, ref, what="tau blr mu_s crossing")
+
+
+@pytest.mark.parametrize("mu_s", [0.9999, 0.9, 0.45, 0.0])
+def test_tau_dt_and_ps_mu_s(mu_s):
+    nu = np.logspace(25, 32, 40)
+    L = 2e46 * u.Unit("erg s-1")
+    ref = orc.tau_dt_mu_s(nu, 0.1, mu_s, 2e46, 0.1, cases.EPS_DT, 1e17, 1e18, u_size=100)
+    got = ab.Absorption.evaluate_tau_dt_mu_s(nu * u.Hz, 0.1, mu_s, L, 0.1, cases.EPS_DT, 1e17 * u.cm,
+                                             1e18 * u.cm, u_size=100)
+    assert_parity(got, ref, what=f"tau dt mu_s={mu_s}")
+    ref = orc.tau_ps_behind_blob_mu_s(nu, 0.1, mu_s, cases.EPS_DT, 0.1 * 2e46, 1e18, u_size=100)
+    got = ab.Absorption.evaluate_tau_ps_behind_blob_mu_s(nu * u.Hz, 0.1, mu_s, cases.EPS_DT, 0.1 * L, 1e18 * u.cm)
+    assert_parity(got, ref, what=f"tau ps mu_s={mu_s}")
+    ref = orc.tau_ps_behind_blob(nu, 0.1, mu_s, cases.EPS_DT, 0.1 * 2e46, 1e18)
+    got = ab.Absorption.evaluate_tau_ps_behind_blob(nu * u.Hz, 0.1, mu_s, cases.EPS_DT, 0.1 * L, 1e18 * u.cm)
+    assert_parity(got, ref, what=f"tau ps closed form mu_s={mu_s}")
+
+
+def test_absorption_dispatch_off_axis():
+    """targets_absorption.py:696-730; DT far away -> point source as in absorption/tests/test_absorption.py:279-334"""
+    from agnpy_b200 import targets
+    L = 2e46 * u.Unit("erg s-1")
+    dt = targets.RingDustTorus(L, 0.1, 1e3 * u.K, R_dt=1e17 * u.cm)
+    ps = targets.PointSourceBehindJet(0.1 * L, dt.epsilon_dt)
+    nu = np.logspace(26, 32, 60) * u.Hz
+    for mu_s in (0.0, 0.45, 0.9):
+        a = ab.Absorption(dt, r=1e18 * u.cm, z=0, mu_s=mu_s).tau(nu)
+        b = ab.Absorption(ps, r=1e18 * u.cm, z=0, mu_s=mu_s).tau(nu)
+        # the reference compares peak height and position (10 %)
+        assert np.isclose(a.max(), b.max(), atol=0, rtol=0.1)
+        assert np.isclose(nu.value[a.argmax()], nu.value[b.argmax()], atol=0, rtol=0.1)
+    assert np.all(ab.Absorption(ps, r=1e18 * u.cm, z=0, mu_s=1).tau(nu) == 0)   # :714
+    blr = targets.SphericalShellBLR(L, 0.024, "Lyalpha", 1e17 * u.cm)
+    nu2 = np.logspace(23.5, 29.5, 50) * u.Hz
+    on = ab.Absorption(blr, r=1.1e16 * u.cm, z=0.859)
+    off = ab.Absorption(blr, r=1.1e16 * u.cm, z=0.859, mu_s=0.9999)
+    t_on, t_off = on.tau(nu2), off.tau(nu2)
+    sel = t_on > 1e-4
+    assert np.allclose(t_off[sel], t_on[sel], atol=0, rtol=0.25)      # absorption tests :336-377
+    disk = targets.SSDisk(cases.M_BH * u.g, L, 1 / 12, 6, 200, R_g_units=True)
+    with pytest.raises(NotImplementedError):
+        ab.Absorption(disk, r=1e17 * u.cm, mu_s=0.9).tau(nu)
