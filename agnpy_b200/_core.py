@@ -79,3 +79,14 @@ def bb_sed_host(variant, models, nu, nu_norm=None, n_R=100):
         variant, n, hptr(models), hptr(nu), nu.size, hptr(nu_norm),
         0 if nu_norm is None else nu_norm.size, int(n_R), hptr(sed)), "agnpy_b200_bb_sed_host")
     return sed
+
+
+def tau_synch_host(models, ne_kind, nu, gamma, ne_table=None, ssa_table=None, n_s=200,
+                   margin_low=1.0e-2, integ=0):
+    nu, gamma = f64(nu), f64(gamma)
+    n = len(models)
+    tau = np.empty((n, nu.size))
+    check(lib().agnpy_b200_tau_synch_host(
+        n, hptr(models), ne_kind, hptr(nu), nu.size, hptr(gamma), gamma.size, hptr(ne_table),
+        hptr(ssa_table), int(n_s), float(margin_low), integ, hptr(tau)), "agnpy_b200_tau_synch_host")
+    return tau

@@ -27,6 +27,7 @@ EXPORTS = [
     "agnpy_b200_ssc_sed", "agnpy_b200_ssc_sed_host",
     "agnpy_b200_ec_sed", "agnpy_b200_ec_sed_host",
     "agnpy_b200_tau", "agnpy_b200_tau_host",
+    "agnpy_b200_tau_synch", "agnpy_b200_tau_synch_host",
     "agnpy_b200_bb_sed", "agnpy_b200_bb_sed_host",
 ]
 
@@ -79,6 +80,9 @@ def lib():
     tau = [ip, ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
     L.agnpy_b200_tau.argtypes = tau + [vp]
     L.agnpy_b200_tau_host.argtypes = tau
+    tsy = [ip, dp, ip, dp, ip, dp, ip, dp, dp, ip, C.c_double, ip, dp]
+    L.agnpy_b200_tau_synch.argtypes = tsy + [vp]
+    L.agnpy_b200_tau_synch_host.argtypes = tsy
     bb = [ip, ip, dp, dp, ip, dp, ip, ip, dp]
     L.agnpy_b200_bb_sed.argtypes = bb + [vp]
     L.agnpy_b200_bb_sed_host.argtypes = bb

@@ -3,7 +3,7 @@ static `evaluate_tau_{ss_disk,blr,dt}` signatures (targets_absorption.py:182-196
 474-486), running on the fused FP64 CUDA kernel K4."""
 import numpy as np
 
-from . import _core, _lib
+from . import _core, _lib, spectra
 from .compton import _target_kind
 from .grids import as_grid, mu_to_integrate, phi_to_integrate
 from .units import strip
@@ -27,8 +27,7 @@ def _tau_call(variant, nu, z, mu_s, tgt, mu, n_a, phi, l_size, off_axis=False):
 
 
 class Absorption:
-    """targets_absorption.py:45-747 (absorption on the blob's own synchrotron photons,
-    `tau_on_synchrotron`, is not part of this build yet and raises)."""
+    """targets_absorption.py:45-747; every branch of the reference's `tau()` dispatch."""
 
     def __init__(self, target, r=None, z=0, mu_s=1):
         self.target = target
@@ -38,7 +37,7 @@ class Absorption:
         self.set_mu()
         self.set_phi()
         self.set_l()
-        if r is None:
+        if r is None and _target_kind(target) != "Blob" and not hasattr(target, "n_e"):
             raise ValueError(
                 "No distance provided for absorption on " + str(target.__class__)
                 + ", this can be only done for Blob class")
@@ -133,6 +132,25 @@ class Absorption:
         return self.evaluate_tau_dt_mu_s(nu, self.z, self.mu_s, t.L_disk, t.xi_dt, t.epsilon_dt,
                                          t.R_dt, self.r, u_size=2 * self.l_size, phi_re=self.phi)
 
+    def tau_on_synchrotron(self, blob, nu, nu_s_size=200, delta_margin_low=1.0e-2):
+        """opacity on the blob's own (self-absorbed) synchrotron photons,
+        targets_absorption.py:629-694"""
+        nu_hz = strip(nu, "Hz", "nu")
+        n_e = blob.n_e
+        kind, par = spectra.describe(n_e, n_e.parameters)
+        gamma = as_grid(blob.gamma_e, "gamma")
+        ne_t = ssa_t = None
+        if kind == _lib.NE_TABLE:
+            g = spectra.snap_boundaries(gamma, par[1], par[2])
+            ne_t, ssa_t = spectra.tables(n_e, n_e.parameters, g, True)
+        models = _lib.make_models(1)
+        _core.model_row(models, 0, z=float(blob.z), d_L=strip(blob.d_L, "cm", "d_L"),
+                        delta_D=float(blob.delta_D), B=strip(blob.B, "G", "B"),
+                        R_b=strip(blob.R_b, "cm", "R_b"), ne=par)
+        tau = _core.tau_synch_host(models, kind, np.ravel(nu_hz), gamma, ne_t, ssa_t, nu_s_size,
+                                   delta_margin_low)
+        return tau[0].reshape(np.shape(nu_hz))
+
     def tau_ss_disk(self, nu):
         """targets_absorption.py:266-282"""
         t = self.target
@@ -156,8 +174,8 @@ class Absorption:
     def tau(self, nu):
         """targets_absorption.py:696-730"""
         kind = _target_kind(self.target)
-        if kind == "Blob":
-            raise NotImplementedError("absorption on synchrotron photons is not built yet")
+        if kind == "Blob" or hasattr(self.target, "n_e"):
+            return self.tau_on_synchrotron(self.target, nu)
         if self.mu_s == 1:
             table = {"PointSourceBehindJet": self.tau_ps_behind_blob, "SSDisk": self.tau_ss_disk,
                      "SphericalShellBLR": self.tau_blr, "RingDustTorus": self.tau_dt}

@@ -193,6 +193,33 @@ int agnpy_b200_tau(int variant, int n_models, const agnpy_model_t* models, const
 }
 
 // ------------------------------------------------------------------------------------------
+int agnpy_b200_tau_synch(int n_models, const agnpy_model_t* models, int ne_kind, const double* nu,
+                         int n_nu, const double* gamma, int n_gamma, const double* ne_table,
+                         const double* ssa_table, int n_s, double delta_margin_low, int integ,
+                         double* tau, void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || n_s < 2 || !models || !nu || !gamma || !tau)
+        return fail(AGNPY_ERR_ARG, "tau_synch: bad sizes or null pointer");
+    if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "tau_synch: bad ne_kind/integ");
+    if (n_s > 65535 || (n_nu + 3) / 4 > 65535) return fail(AGNPY_ERR_ARG, "tau_synch: grid too large");
+    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table || !ssa_table))
+        return fail(AGNPY_ERR_ARG, "tau_synch: AGNPY_NE_TABLE needs n_models == 1 and both tables");
+    integ = plain_integ(integ);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t per = tau_synch_workspace_bytes(1, n_nu, n_gamma, n_s);
+    int chunk = chunk_models(per, n_models);
+    double* ws = (double*)workspace(per * chunk, stream);
+    if (!ws) return fail(AGNPY_ERR_NOMEM, "tau_synch: workspace");
+    for (int m0 = 0; m0 < n_models; m0 += chunk) {
+        int nm = std::min(chunk, n_models - m0);
+        if (int rc = run_tau_synch(models + m0, nm, ne_kind, nu, n_nu, gamma, n_gamma, ne_table, ssa_table,
+                                   n_s, delta_margin_low, integ, tau + (size_t)m0 * n_nu, ws, stream))
+            return rc;
+    }
+    return AGNPY_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 int agnpy_b200_bb_sed(int variant, int n_models, const agnpy_model_t* models, const double* nu,
                       int n_nu, const double* nu_norm, int n_norm, int n_R, double* sed,
                       void* stream_) {
@@ -432,6 +459,29 @@ int agnpy_b200_bb_sed_host(int variant, int n_models, const agnpy_model_t* model
     if (int rc = io.upload()) return rc;
     if (int rc = agnpy_b200_bb_sed(variant, n_models, io.dev<agnpy_model_t>(i_m), io.dev<double>(i_nu),
                                    n_nu, io.dev<double>(i_nn), n_norm, n_R, io.dev<double>(o_sed), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_tau_synch_host(int n_models, const agnpy_model_t* models, int ne_kind,
+                              const double* nu, int n_nu, const double* gamma, int n_gamma,
+                              const double* ne_table, const double* ssa_table, int n_s,
+                              double delta_margin_low, int integ, double* tau) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || !models || !nu || !gamma || !tau)
+        return fail(AGNPY_ERR_ARG, "tau_synch_host: bad sizes or null pointer");
+    size_t out_n = (size_t)n_models * n_nu;
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int i_sa = io.in(ssa_table, 8 * (size_t)n_gamma);
+    int o_tau = io.out(tau, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_tau_synch(n_models, io.dev<agnpy_model_t>(i_m), ne_kind, io.dev<double>(i_nu),
+                                      n_nu, io.dev<double>(i_g), n_gamma, io.dev<double>(i_ne),
+                                      io.dev<double>(i_sa), n_s, delta_margin_low, integ,
+                                      io.dev<double>(o_tau), io.st))
         return rc;
     return io.download();
 }

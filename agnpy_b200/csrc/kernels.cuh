@@ -10,7 +10,7 @@ void launch_prep_gamma(const agnpy_model_t* models, int n_models, int ne_kind, c
 
 int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                  const double* tab, int n_gamma, int ssa, int integ, int out_mode, double* out,
-                 double* tau_out, double* eps_out, cudaStream_t stream);
+                 double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride = 0);
 
 int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,
@@ -27,6 +27,12 @@ size_t tau_workspace_bytes(int variant, int n_models, int n_nu, int n_a, int n_p
 int run_tau(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
             const double* mu, int n_a, const double* phi, int n_phi, const double* l_unit, int n_l,
             double* tau, double* ws, cudaStream_t stream);
+
+// opacity on the blob's own synchrotron photons (targets_absorption.py:629-694)
+size_t tau_synch_workspace_bytes(int n_models, int n_nu, int n_gamma, int n_s);
+int run_tau_synch(const agnpy_model_t* models, int n_models, int ne_kind, const double* nu, int n_nu,
+                  const double* gamma, int n_gamma, const double* ne_table, const double* ssa_table,
+                  int n_s, double margin_low, int integ, double* tau, double* ws, cudaStream_t stream);
 
 int run_bb(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
            const double* nu_norm, int n_norm, int n_R, double* sed, cudaStream_t stream);

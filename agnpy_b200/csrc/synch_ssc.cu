@@ -70,13 +70,15 @@ void launch_prep_gamma(const agnpy_model_t* models, int n_models, int ne_kind, c
 // ---------------------------------------------------------------------------------------------
 // K1: synchrotron SED (+ SSA).  grid = (n_nu, n_models), one block per output frequency.
 // out_mode 0: sed = nu F_nu;  out_mode 1 (SSC seed stage): U = u_synch / eps^2 with
-// u_synch of blob.py:395-404, plus eps written to eps_out.
+// u_synch of blob.py:395-404, plus eps written to eps_out;  out_mode 2 (opacity on the
+// synchrotron field): photon density n_synch(eps) of targets_absorption.py:671-684, plus eps.
 // ---------------------------------------------------------------------------------------------
 template <int INTEG>
 __global__ void __launch_bounds__(128) synch_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
     const double* __restrict__ tab, int n_gamma, int ssa, int out_mode,
-    double* __restrict__ out, double* __restrict__ tau_out, double* __restrict__ eps_out) {
+    double* __restrict__ out, double* __restrict__ tau_out, double* __restrict__ eps_out,
+    int nu_stride) {
     extern __shared__ double sh[];
     __shared__ double red[32];
     const int m = blockIdx.y, i = blockIdx.x;
@@ -84,7 +86,8 @@ __global__ void __launch_bounds__(128) synch_kernel(
     const double* gs = tab + (size_t)m * 3 * n_gamma;
     const double* Ne = gs + n_gamma;
     const double* Sa = gs + 2 * n_gamma;
-    const double eps = nu_to_eps(nu[i], M.z, M.delta_D);
+    // nu_stride = 0: one frequency grid for all models; n_nu: a grid per model
+    const double eps = nu_to_eps(nu[(size_t)m * nu_stride + i], M.z, M.delta_D);
     const double B = M.B;
     // synchrotron.py:35-47: x = 4 pi eps m_e^2 c^3 / (3 e B h gamma^2)
     const double xnum = 4.0 * kPi * eps * (kMe * kMe) * (kC * kC * kC);
@@ -136,6 +139,13 @@ __global__ void __launch_bounds__(128) synch_kernel(
         }
         if (out_mode == 0) {
             out[(size_t)m * n_nu + i] = sed;
+        } else if (out_mode == 2) {
+            // photon density of the synchrotron field per unit eps, targets_absorption.py:671-684
+            double n_synch = (3.0 * (M.d_L * M.d_L) * sed) /
+                             (kC * (M.R_b * M.R_b) * (M.delta_D * M.delta_D * M.delta_D * M.delta_D) *
+                              (eps * eps) * kMe * (kC * kC));
+            out[(size_t)m * n_nu + i] = n_synch * (3.0 / 4.0);
+            eps_out[(size_t)m * n_nu + i] = eps;
         } else {
             // blob.py:395-404 then the 1/eps^2 of synchrotron_self_compton.py:152
             double u = (3.0 * (M.d_L * M.d_L) * sed) /
@@ -149,11 +159,11 @@ __global__ void __launch_bounds__(128) synch_kernel(
 
 int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                  const double* tab, int n_gamma, int ssa, int integ, int out_mode, double* out,
-                 double* tau_out, double* eps_out, cudaStream_t stream) {
+                 double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride) {
     dim3 grid(n_nu, n_models);
     if (integ == AGNPY_INTEG_TRAPZ) {
         synch_kernel<AGNPY_INTEG_TRAPZ><<<grid, 128, 0, stream>>>(
-            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out);
+            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride);
     } else {
         size_t smem = 2 * (size_t)n_gamma * sizeof(double);
         if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for trapz_loglog");
@@ -161,7 +171,7 @@ int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, in
             cudaFuncSetAttribute(synch_kernel<AGNPY_INTEG_LOGLOG>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         synch_kernel<AGNPY_INTEG_LOGLOG><<<grid, 128, smem, stream>>>(
-            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out);
+            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride);
     }
     note_launch();
     return AGNPY_OK;

@@ -212,13 +212,14 @@ __device__ __forceinline__ double sigma_shape(double s, double inv_s) {
     return (s < 1.0) ? 0.0 : v;
 }
 
+constexpr int kTauOnSynch = 100;  // internal variant id of the finish kernel
 constexpr int kTauTN = 4;        // frequencies per thread
 constexpr int kTauSlice = 4096;  // table entries per block
 
 // grid = (n_slices, ceil(n_nu/TN), n_models); part[m][i][slice]
 __global__ void __launch_bounds__(256) tau_main_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
-    const double* __restrict__ table, int n_t, double* __restrict__ part) {
+    const double* __restrict__ table, int n_t, double* __restrict__ part, int blob_frame) {
     __shared__ double red[32];
     const int slice = blockIdx.x, m = blockIdx.z, S = gridDim.x;
     const int i0 = blockIdx.y * kTauTN;
@@ -231,7 +232,9 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
 #pragma unroll
     for (int q = 0; q < kTauTN; ++q) {
         int i = min(i0 + q, n_nu - 1);
-        e1[q] = nu_to_eps(nu[i], M.z, 1.0);  // targets_absorption.py:331: no Doppler factor
+        // targets_absorption.py:331: no Doppler factor for the external fields; :647 the blob
+        // frame for the synchrotron field
+        e1[q] = nu_to_eps(nu[i], M.z, blob_frame ? M.delta_D : 1.0);
         ie1[q] = 1.0 / e1[q];
         acc[q] = 0.0;
     }
@@ -275,11 +278,92 @@ __global__ void __launch_bounds__(128) tau_finish_kernel(
         pref = (g[0] * g[1]) / (8.0 * (kPi * kPi) * g[2] * kMe * c3);
     else if (variant == AGNPY_TAU_PS_BEHIND_BLOB || variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S)  // :118, 172
         pref = g[1] / (4.0 * kPi * g[0] * kMe * c3);
+    else if (variant == kTauOnSynch)  // :694
+        pref = 2.0 * M.R_b;
     else {  // :263
         double R_g = kG * g[0] / (kC * kC);
         pref = 3.0 * g[1] / ((4.0 * kPi) * (4.0 * kPi) * g[2] * kMe * c3 * R_g);
     }
     tau[(size_t)m * n_nu + i] = pref * integral;
+}
+
+// ---- opacity on the blob's own synchrotron photons, targets_absorption.py:629-694 --------------
+// frequencies of the synchrotron field, one grid per model: logspace between the delta-approximation
+// peaks of gamma_min and gamma_max (synchrotron.py:27-32) with margins, blob frame -> observer
+__global__ void __launch_bounds__(128) tau_synch_nu_kernel(
+    const agnpy_model_t* __restrict__ models, int ne_kind, int n_s, double margin_low,
+    double* __restrict__ nu_s_obs) {
+    const int m = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_s) return;
+    const agnpy_model_t& M = models[m];
+    double gmin, gmax;
+    if (ne_kind == AGNPY_NE_TABLE) { gmin = M.ne[1]; gmax = M.ne[2]; }
+    else ne_bounds(ne_kind, M.ne, gmin, gmax);
+    double peak = kE * M.B / (2.0 * kPi * kMe * kC);
+    double lo = log10(peak * (gmin * gmin) * margin_low), hi = log10(peak * (gmax * gmax) * 1.0e2);
+    double y = (n_s == 1) ? lo : (j == n_s - 1 ? hi : (double)j * ((hi - lo) / (double)(n_s - 1)) + lo);
+    double nu_s = pow(10.0, y);
+    nu_s_obs[(size_t)m * n_s + j] = nu_s * M.delta_D / (1.0 + M.z);
+}
+
+// table entries of the tau kernel from the photon density: s = eps eps_1 / 2 (:690)
+__global__ void __launch_bounds__(128) tau_synch_table_kernel(
+    const double* __restrict__ n_synch, const double* __restrict__ eps, int n_s,
+    double* __restrict__ table) {
+    const int m = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_s) return;
+    const double* e = eps + (size_t)m * n_s;
+    double* row = table + (size_t)m * 4 * n_s;
+    row[j] = e[j];
+    row[n_s + j] = 0.5;
+    row[2 * (size_t)n_s + j] = 1.0 / (e[j] * 0.5);
+    row[3 * (size_t)n_s + j] = trapz_weight(e, j, n_s) * n_synch[(size_t)m * n_s + j];
+}
+
+size_t tau_synch_workspace_bytes(int n_models, int n_nu, int n_gamma, int n_s) {
+    size_t S = ((size_t)n_s + kTauSlice - 1) / kTauSlice;
+    return (3 * (size_t)n_gamma + 7 * (size_t)n_s + (size_t)n_nu * S) * sizeof(double) * (size_t)n_models;
+}
+
+int run_tau_synch(const agnpy_model_t* models, int n_models, int ne_kind, const double* nu, int n_nu,
+                  const double* gamma, int n_gamma, const double* ne_table, const double* ssa_table,
+                  int n_s, double margin_low, int integ, double* tau, double* ws, cudaStream_t stream) {
+    const size_t M = (size_t)n_models;
+    int S = (n_s + kTauSlice - 1) / kTauSlice;
+    double* tab = ws;
+    double* nu_s = tab + M * 3 * n_gamma;
+    double* nsyn = nu_s + M * n_s;
+    double* eps = nsyn + M * n_s;
+    double* table = eps + M * n_s;
+    double* part = table + M * 4 * n_s;
+    launch_prep_gamma(models, n_models, ne_kind, gamma, n_gamma, ne_table, ssa_table, 0, tab, stream);
+    {
+        dim3 grid((n_s + 127) / 128, n_models);
+        tau_synch_nu_kernel<<<grid, 128, 0, stream>>>(models, ne_kind, n_s, margin_low, nu_s);
+        note_launch();
+    }
+    // self-absorbed synchrotron SED at those frequencies -> photon density (:668-687)
+    if (int rc = launch_synch(models, n_models, nu_s, n_s, tab, n_gamma, 1, integ, 2, nsyn, nullptr, eps,
+                              stream, n_s))
+        return rc;
+    {
+        dim3 grid((n_s + 127) / 128, n_models);
+        tau_synch_table_kernel<<<grid, 128, 0, stream>>>(nsyn, eps, n_s, table);
+        note_launch();
+    }
+    {
+        dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
+        timing_begin(stream);
+        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_s, part, 1);
+        timing_end(stream);
+        note_launch();
+    }
+    {
+        dim3 grid((n_nu + 127) / 128, n_models);
+        tau_finish_kernel<<<grid, 128, 0, stream>>>(kTauOnSynch, models, n_nu, part, S, tau);
+        note_launch();
+    }
+    return check_last("tau_synch");
 }
 
 static int tau_n_t(int variant, int n_a, int n_phi, int n_l) {
@@ -319,7 +403,7 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
     {
         dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
         timing_begin(stream);
-        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, part);
+        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, part, 0);
         timing_end(stream);
         note_launch();
     }

@@ -162,6 +162,19 @@ int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
                         const double* phi, int n_phi, const double* l_unit, int n_l,
                         double* tau);
 
+/* opacity on the blob's own synchrotron photons
+ * replaces Absorption.tau_on_synchrotron   agnpy/absorption/targets_absorption.py:629-694
+ * (self-absorbed synchrotron spectrum on n_s frequencies between the delta-approximation peaks of
+ * gamma_min and gamma_max, photon density, sigma(s) folded over it); gamma = blob.gamma_e. */
+int agnpy_b200_tau_synch(int n_models, const agnpy_model_t* models, int ne_kind, const double* nu,
+                         int n_nu, const double* gamma, int n_gamma, const double* ne_table,
+                         const double* ssa_table, int n_s, double delta_margin_low, int integ,
+                         double* tau, void* stream);
+int agnpy_b200_tau_synch_host(int n_models, const agnpy_model_t* models, int ne_kind,
+                              const double* nu, int n_nu, const double* gamma, int n_gamma,
+                              const double* ne_table, const double* ssa_table, int n_s,
+                              double delta_margin_low, int integ, double* tau);
+
 /* ---- thermal black-body SEDs (fit-wrapper components) -----------------------------------------
  * replaces SSDisk.evaluate_multi_T_bb_sed / evaluate_multi_T_bb_norm_sed
  *          agnpy/targets/targets.py:350-415

@@ -932,3 +932,24 @@ def tau_dt_mu_s(nu, z, mu_s, L_disk, xi_dt, epsilon_dt, R_dt, r, u_size=100, phi
     integral = trapz(i_phi, uu, axis=0)
     prefactor = (L_disk * xi_dt) / (8 * np.pi**2 * epsilon_dt * M_E * C_LIGHT**3)
     return prefactor * integral
+
+
+def tau_on_synchrotron(nu, z, d_L, delta_D, B, R_b, ne_kind, ne_args, gamma, nu_s_size=200,
+                       delta_margin_low=1.0e-2, integrator="trapz"):
+    """targets_absorption.py:629-694 (`Synchrotron(blob, ssa=True).sed_flux` uses
+    blob.gamma_e = `gamma` and the Synchrotron default integrator np.trapz)"""
+    gmin, gmax = _gamma_bounds(ne_kind, ne_args)
+    epsilon1 = nu_to_epsilon_prime(nu, z, delta_D)
+    nu_s_min = nu_synch_peak(B, gmin) * delta_margin_low
+    nu_s_max = nu_synch_peak(B, gmax) * 1.0e2
+    nu_s = np.logspace(np.log10(nu_s_min), np.log10(nu_s_max), nu_s_size)
+    nu_s_obs = nu_s * delta_D / (1 + z)
+    epsilon = nu_to_epsilon_prime(nu_s_obs, z, delta_D)
+    sed_synch = synch_sed_flux(nu_s_obs, z, d_L, delta_D, B, R_b, ne_kind, ne_args, ssa=True,
+                               integrator=integrator, gamma=gamma)
+    n_synch = (3 * np.power(d_L, 2) * sed_synch) / (
+        C_LIGHT * np.power(R_b, 2) * np.power(delta_D, 4) * epsilon**2 * M_E * C_LIGHT**2)
+    n_synch = n_synch * (3 / 4)
+    _epsilon, _epsilon1 = broadcast_axes(epsilon, epsilon1)
+    _s = _epsilon * _epsilon1 / 2
+    return 2 * R_b * trapz(n_synch[..., np.newaxis] * sigma_gg(_s), epsilon, axis=0)

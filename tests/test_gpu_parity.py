@@ -400,3 +400,23 @@ def test_absorption_dispatch_off_axis():
     disk = targets.SSDisk(cases.M_BH * u.g, L, 1 / 12, 6, 200, R_g_units=True)
     with pytest.raises(NotImplementedError):
         ab.Absorption(disk, r=1e17 * u.cm, mu_s=0.9).tau(nu)
+
+
+@pytest.mark.parametrize("kind", ["PowerLaw", "BrokenPowerLaw", "LogParabola"])
+def test_tau_on_synchrotron(kind):
+    """targets_absorption.py:629-694.  The photon field is the self-absorbed synchrotron SED,
+    whose attenuation the reference evaluates with a cancelling formula: parity is
+    asserted where the SSA optical depth is not in the ill-conditioned window, 1e-6 overall."""
+    from agnpy_b200 import targets
+    args = {"PowerLaw": (1e-2, 2.5, 10.0, 1e5), "BrokenPowerLaw": (1e-3, 2.0, 3.2, 1e3, 10.0, 1e6),
+            "LogParabola": (1e-2, 2.2, 0.3, 1e3, 5.0, 1e6)}[kind]
+    ne = ne_obj(kind, (args[0] * u.Unit("cm-3"),) + tuple(args[1:]))
+    blob = targets.Blob(1e16 * u.cm, 0.5, 1e28 * u.cm, 20, 20, 0.5 * u.G, ne)
+    nu = np.logspace(22, 31, 50)
+    ref = orc.tau_on_synchrotron(nu, 0.5, 1e28, 20, 0.5, 1e16, kind, args, blob.gamma_e)
+    got = ab.Absorption(blob, z=0.5).tau(nu * u.Hz)
+    assert got.shape == (50,) and np.count_nonzero(ref) > 10
+    assert_parity(got, ref, rtol=1e-6, what=f"tau on synchrotron {kind}")
+    got2 = ab.Absorption(blob).tau_on_synchrotron(blob, nu * u.Hz, nu_s_size=120, delta_margin_low=1e-3)
+    ref2 = orc.tau_on_synchrotron(nu, 0.5, 1e28, 20, 0.5, 1e16, kind, args, blob.gamma_e, 120, 1e-3)
+    assert_parity(got2, ref2, rtol=1e-6, what=f"tau on synchrotron {kind} (120, 1e-3)")
