@@ -4,10 +4,10 @@ from .absorption import Absorption
 from .compton import ExternalCompton, SynchrotronSelfCompton
 from .grids import (gamma_e_to_integrate, mu_to_integrate, nu_to_integrate, phi_to_integrate,
                     trapz_loglog, trapz_prefix)
-from .synchrotron import Synchrotron
+from .synchrotron import ProtonSynchrotron, Synchrotron
 from .units import Quantity, u
 
-__all__ = ["Synchrotron", "SynchrotronSelfCompton", "ExternalCompton", "Absorption",
+__all__ = ["Synchrotron", "ProtonSynchrotron", "SynchrotronSelfCompton", "ExternalCompton", "Absorption",
            "trapz_loglog", "trapz_prefix", "gamma_e_to_integrate", "nu_to_integrate", "mu_to_integrate",
            "phi_to_integrate", "Quantity", "u"]
 __version__ = "0.1.0"

@@ -90,3 +90,23 @@ def tau_synch_host(models, ne_kind, nu, gamma, ne_table=None, ssa_table=None, n_
         n, hptr(models), ne_kind, hptr(nu), nu.size, hptr(gamma), gamma.size, hptr(ne_table),
         hptr(ssa_table), int(n_s), float(margin_low), integ, hptr(tau)), "agnpy_b200_tau_synch_host")
     return tau
+
+
+def proton_synch_sed_host(models, ne_kind, nu, gamma, ne_table=None, integ=0):
+    nu, gamma = f64(nu), f64(gamma)
+    n = len(models)
+    sed = np.empty((n, nu.size))
+    check(lib().agnpy_b200_proton_synch_sed_host(
+        n, hptr(models), ne_kind, hptr(nu), nu.size, hptr(gamma), gamma.size, hptr(ne_table), integ,
+        hptr(sed)), "agnpy_b200_proton_synch_sed_host")
+    return sed
+
+
+def ssc_loss_rate_host(models, ne_kind, gamma_eval, nu_seed, gamma, ne_table=None):
+    gamma_eval, nu_seed, gamma = f64(gamma_eval), f64(nu_seed), f64(gamma)
+    n = len(models)
+    out = np.empty((n, gamma_eval.size))
+    check(lib().agnpy_b200_ssc_loss_rate_host(
+        n, hptr(models), ne_kind, hptr(gamma_eval), gamma_eval.size, hptr(nu_seed), nu_seed.size,
+        hptr(gamma), gamma.size, hptr(ne_table), hptr(out)), "agnpy_b200_ssc_loss_rate_host")
+    return out

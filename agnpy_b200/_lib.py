@@ -28,6 +28,8 @@ EXPORTS = [
     "agnpy_b200_ec_sed", "agnpy_b200_ec_sed_host",
     "agnpy_b200_tau", "agnpy_b200_tau_host",
     "agnpy_b200_tau_synch", "agnpy_b200_tau_synch_host",
+    "agnpy_b200_proton_synch_sed", "agnpy_b200_proton_synch_sed_host",
+    "agnpy_b200_ssc_loss_rate", "agnpy_b200_ssc_loss_rate_host",
     "agnpy_b200_bb_sed", "agnpy_b200_bb_sed_host",
 ]
 
@@ -80,6 +82,12 @@ def lib():
     tau = [ip, ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
     L.agnpy_b200_tau.argtypes = tau + [vp]
     L.agnpy_b200_tau_host.argtypes = tau
+    psy = [ip, dp, ip, dp, ip, dp, ip, dp, ip, dp]
+    L.agnpy_b200_proton_synch_sed.argtypes = psy + [vp]
+    L.agnpy_b200_proton_synch_sed_host.argtypes = psy
+    lr = [ip, dp, ip, dp, ip, dp, ip, dp, ip, dp, dp]
+    L.agnpy_b200_ssc_loss_rate.argtypes = lr + [vp]
+    L.agnpy_b200_ssc_loss_rate_host.argtypes = lr
     tsy = [ip, dp, ip, dp, ip, dp, ip, dp, dp, ip, C.c_double, ip, dp]
     L.agnpy_b200_tau_synch.argtypes = tsy + [vp]
     L.agnpy_b200_tau_synch_host.argtypes = tsy

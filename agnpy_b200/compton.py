@@ -32,6 +32,21 @@ class SynchrotronSelfCompton:
                                  ssa_t, ssa, integrator_code(integrator))
         return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
 
+    def electron_energy_loss_rate(self, gamma):
+        """Klein-Nishina corrected SSC loss rate [erg s-1] at the Lorentz factors `gamma`,
+        synchrotron_self_compton.py:43-71 (seed spectrum on utils/math.py:6-7 default grids)"""
+        b = self.blob
+        kind, par = spectra.describe(b.n_e, b.n_e.parameters)
+        grid = as_grid(gamma_e_to_integrate, "gamma")
+        ne_t = None
+        if kind == _lib.NE_TABLE:
+            ne_t, _ = spectra.tables(b.n_e, b.n_e.parameters,
+                                     spectra.snap_boundaries(grid, par[1], par[2]), False)
+        models = _blob_models(b.z, b.d_L, b.delta_D, b.B, b.R_b, par)
+        g = np.asarray(gamma, dtype=np.float64)
+        out = _core.ssc_loss_rate_host(models, kind, np.ravel(g), nu_to_integrate, grid, ne_t)
+        return wrap(out[0].reshape(g.shape), "erg s-1")
+
     def sed_flux(self, nu):
         """synchrotron_self_compton.py:160-175"""
         b = self.blob

@@ -131,6 +131,67 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
 }
 
 // ------------------------------------------------------------------------------------------
+int agnpy_b200_proton_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
+                                const double* nu, int n_nu, const double* gamma, int n_gamma,
+                                const double* ne_table, int integ, double* sed, void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || !models || !nu || !gamma || !sed)
+        return fail(AGNPY_ERR_ARG, "proton_synch_sed: bad sizes or null pointer");
+    if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "proton_synch_sed: bad ne_kind/integ");
+    if (n_nu > 65535) return fail(AGNPY_ERR_ARG, "proton_synch_sed: n_nu > 65535");
+    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table))
+        return fail(AGNPY_ERR_ARG, "proton_synch_sed: AGNPY_NE_TABLE needs n_models == 1 and a table");
+    integ = plain_integ(integ);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t per = 3 * (size_t)n_gamma * sizeof(double);
+    int chunk = chunk_models(per, n_models);
+    double* tab = (double*)workspace(per * chunk, stream);
+    if (!tab) return fail(AGNPY_ERR_NOMEM, "proton_synch_sed: workspace");
+    for (int m0 = 0; m0 < n_models; m0 += chunk) {
+        int nm = std::min(chunk, n_models - m0);
+        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, nullptr, 0, tab, stream);
+        timing_begin(stream);
+        int rc = launch_synch(models + m0, nm, nu, n_nu, tab, n_gamma, 0, integ, 0,
+                              sed + (size_t)m0 * n_nu, nullptr, nullptr, stream, 0, 1);
+        timing_end(stream);
+        if (rc) return rc;
+    }
+    return check_last("proton_synch_sed");
+}
+
+// ------------------------------------------------------------------------------------------
+int agnpy_b200_ssc_loss_rate(int n_models, const agnpy_model_t* models, int ne_kind,
+                             const double* gamma_eval, int n_eval, const double* nu_seed, int n_seed,
+                             const double* gamma, int n_gamma, const double* ne_table, double* out,
+                             void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_eval < 1 || n_seed < 2 || n_gamma < 2 || !models || !gamma_eval || !nu_seed ||
+        !gamma || !out)
+        return fail(AGNPY_ERR_ARG, "ssc_loss_rate: bad sizes or null pointer");
+    if (bad_kind(ne_kind)) return fail(AGNPY_ERR_ARG, "ssc_loss_rate: bad ne_kind");
+    if (n_eval > 65535 || n_seed > 65535) return fail(AGNPY_ERR_ARG, "ssc_loss_rate: grid too large");
+    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table))
+        return fail(AGNPY_ERR_ARG, "ssc_loss_rate: AGNPY_NE_TABLE needs n_models == 1 and a table");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t per = (3 * (size_t)n_gamma + 2 * (size_t)n_seed) * sizeof(double);
+    int chunk = chunk_models(per, n_models);
+    double* ws = (double*)workspace(per * chunk, stream);
+    if (!ws) return fail(AGNPY_ERR_NOMEM, "ssc_loss_rate: workspace");
+    for (int m0 = 0; m0 < n_models; m0 += chunk) {
+        int nm = std::min(chunk, n_models - m0);
+        double* tab = ws;
+        double* U = tab + (size_t)nm * 3 * n_gamma;
+        double* es = U + (size_t)nm * n_seed;
+        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, nullptr, 0, tab, stream);
+        if (int rc = launch_synch(models + m0, nm, nu_seed, n_seed, tab, n_gamma, 0, AGNPY_INTEG_TRAPZ, 1,
+                                  U, nullptr, es, stream))
+            return rc;
+        launch_ssc_loss_rate(nm, gamma_eval, n_eval, U, es, n_seed, out + (size_t)m0 * n_eval, stream);
+    }
+    return check_last("ssc_loss_rate");
+}
+
+// ------------------------------------------------------------------------------------------
 int agnpy_b200_ec_sed(int variant, int n_models, const agnpy_model_t* models, int ne_kind,
                       const double* nu, int n_nu, const double* gamma, int n_gamma,
                       const double* mu, int n_mu, const double* phi, int n_phi,
@@ -482,6 +543,47 @@ int agnpy_b200_tau_synch_host(int n_models, const agnpy_model_t* models, int ne_
                                       n_nu, io.dev<double>(i_g), n_gamma, io.dev<double>(i_ne),
                                       io.dev<double>(i_sa), n_s, delta_margin_low, integ,
                                       io.dev<double>(o_tau), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_proton_synch_sed_host(int n_models, const agnpy_model_t* models, int ne_kind,
+                                     const double* nu, int n_nu, const double* gamma, int n_gamma,
+                                     const double* ne_table, int integ, double* sed) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || n_gamma < 2 || !models || !nu || !gamma || !sed)
+        return fail(AGNPY_ERR_ARG, "proton_synch_sed_host: bad sizes or null pointer");
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int o_sed = io.out(sed, 8 * (size_t)n_models * n_nu);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_proton_synch_sed(n_models, io.dev<agnpy_model_t>(i_m), ne_kind,
+                                             io.dev<double>(i_nu), n_nu, io.dev<double>(i_g), n_gamma,
+                                             io.dev<double>(i_ne), integ, io.dev<double>(o_sed), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_ssc_loss_rate_host(int n_models, const agnpy_model_t* models, int ne_kind,
+                                  const double* gamma_eval, int n_eval, const double* nu_seed,
+                                  int n_seed, const double* gamma, int n_gamma,
+                                  const double* ne_table, double* out) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_eval < 1 || n_seed < 2 || n_gamma < 2 || !models || !gamma_eval || !nu_seed ||
+        !gamma || !out)
+        return fail(AGNPY_ERR_ARG, "ssc_loss_rate_host: bad sizes or null pointer");
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_ge = io.in(gamma_eval, 8 * (size_t)n_eval);
+    int i_sd = io.in(nu_seed, 8 * (size_t)n_seed), i_g = io.in(gamma, 8 * (size_t)n_gamma);
+    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int o = io.out(out, 8 * (size_t)n_models * n_eval);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_ssc_loss_rate(n_models, io.dev<agnpy_model_t>(i_m), ne_kind, io.dev<double>(i_ge),
+                                          n_eval, io.dev<double>(i_sd), n_seed, io.dev<double>(i_g), n_gamma,
+                                          io.dev<double>(i_ne), io.dev<double>(o), io.st))
         return rc;
     return io.download();
 }

@@ -17,6 +17,8 @@ namespace agb {
 constexpr double kC = 29979245800.0;
 constexpr double kH = 6.62607015e-27;
 constexpr double kMe = 9.1093837015e-28;
+constexpr double kMp = 1.67262192369e-24;
+constexpr double kMpc2 = 0.0015032776159851257;  // m_p * c**2
 constexpr double kE = 4.803204712570263e-10;
 constexpr double kSigmaT = 6.6524587321e-25;
 constexpr double kG = 6.6743e-08;

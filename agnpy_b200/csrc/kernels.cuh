@@ -10,7 +10,11 @@ void launch_prep_gamma(const agnpy_model_t* models, int n_models, int ne_kind, c
 
 int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                  const double* tab, int n_gamma, int ssa, int integ, int out_mode, double* out,
-                 double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride = 0);
+                 double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride = 0,
+                 int proton = 0);
+
+int launch_ssc_loss_rate(int n_models, const double* gamma_eval, int n_eval, const double* U_seed,
+                         const double* eps_seed, int n_seed, double* out, cudaStream_t stream);
 
 int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,

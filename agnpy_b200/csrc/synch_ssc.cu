@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) synch_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
     const double* __restrict__ tab, int n_gamma, int ssa, int out_mode,
     double* __restrict__ out, double* __restrict__ tau_out, double* __restrict__ eps_out,
-    int nu_stride) {
+    int nu_stride, int proton) {
     extern __shared__ double sh[];
     __shared__ double red[32];
     const int m = blockIdx.y, i = blockIdx.x;
@@ -87,10 +87,15 @@ __global__ void __launch_bounds__(128) synch_kernel(
     const double* Ne = gs + n_gamma;
     const double* Sa = gs + 2 * n_gamma;
     // nu_stride = 0: one frequency grid for all models; n_nu: a grid per model
-    const double eps = nu_to_eps(nu[(size_t)m * nu_stride + i], M.z, M.delta_D);
+    // proton synchrotron (proton_synchrotron.py:118-127): same arithmetic with m_p, and the
+    // dimensionless energy in units of m_p c^2 (conversion.py:14-35)
+    const double mass = proton ? kMp : kMe;
+    const double nu_i = nu[(size_t)m * nu_stride + i];
+    const double eps = proton ? (1.0 + M.z) * (kH * nu_i / kMpc2) / M.delta_D
+                              : nu_to_eps(nu_i, M.z, M.delta_D);
     const double B = M.B;
-    // synchrotron.py:35-47: x = 4 pi eps m_e^2 c^3 / (3 e B h gamma^2)
-    const double xnum = 4.0 * kPi * eps * (kMe * kMe) * (kC * kC * kC);
+    // synchrotron.py:35-47: x = 4 pi eps m^2 c^3 / (3 e B h gamma^2)
+    const double xnum = 4.0 * kPi * eps * (mass * mass) * (kC * kC * kC);
     const double xden = 3.0 * kE * B * kH;
     const double prefP = sqrt(3.0) * (kE * kE * kE) * B / kH;  // :59
     double acc = 0.0, acc_ssa = 0.0;
@@ -159,11 +164,11 @@ __global__ void __launch_bounds__(128) synch_kernel(
 
 int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                  const double* tab, int n_gamma, int ssa, int integ, int out_mode, double* out,
-                 double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride) {
+                 double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride, int proton) {
     dim3 grid(n_nu, n_models);
     if (integ == AGNPY_INTEG_TRAPZ) {
         synch_kernel<AGNPY_INTEG_TRAPZ><<<grid, 128, 0, stream>>>(
-            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride);
+            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride, proton);
     } else {
         size_t smem = 2 * (size_t)n_gamma * sizeof(double);
         if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for trapz_loglog");
@@ -171,7 +176,7 @@ int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, in
             cudaFuncSetAttribute(synch_kernel<AGNPY_INTEG_LOGLOG>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         synch_kernel<AGNPY_INTEG_LOGLOG><<<grid, 128, smem, stream>>>(
-            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride);
+            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride, proton);
     }
     note_launch();
     return AGNPY_OK;
@@ -334,6 +339,41 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
         ssc_kernel<AGNPY_INTEG_LOGLOG><<<grid, 256, smem, stream>>>(
             models, nu, n_nu, tab, n_gamma, U_seed, eps_seed, n_seed, out);
     }
+    note_launch();
+    return AGNPY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSC energy-loss rate of the electrons (Klein-Nishina corrected, Moderski et al. 2005),
+// compton/synchrotron_self_compton.py:43-71: for every requested gamma,
+//   -dE/dt = 4/3 sigma_T c gamma^2 * trapz(f_KN(4 gamma eps) u_synch(eps), eps),
+// u_synch from the (not self-absorbed) synchrotron SED on the seed grid.  grid = (n_eval, models).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ssc_loss_rate_kernel(
+    const double* __restrict__ gamma_eval, int n_eval, const double* __restrict__ U_seed,
+    const double* __restrict__ eps_seed, int n_seed, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int m = blockIdx.y, i = blockIdx.x;
+    const double g = gamma_eval[i];
+    const double* Us = U_seed + (size_t)m * n_seed;   // u_synch / eps^2 (out_mode 1)
+    const double* es = eps_seed + (size_t)m * n_seed;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < n_seed; j += blockDim.x) {
+        double eps = es[j];
+        double u = Us[j] * (eps * eps);
+        double b = 4.0 * g * eps;
+        double f_KN = (b < 1e4) ? 1.0 / pow(1.0 + b, 1.5)
+                                : (9.0 / (2.0 * (b * b))) * (clipped_log(b) - 11.0 / 6.0);
+        acc = fma(trapz_weight(es, j, n_seed), f_KN * u, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[(size_t)m * n_eval + i] = (4.0 / 3.0) * kSigmaT * kC * acc * (g * g);
+}
+
+int launch_ssc_loss_rate(int n_models, const double* gamma_eval, int n_eval, const double* U_seed,
+                         const double* eps_seed, int n_seed, double* out, cudaStream_t stream) {
+    dim3 grid(n_eval, n_models);
+    ssc_loss_rate_kernel<<<grid, 128, 0, stream>>>(gamma_eval, n_eval, U_seed, eps_seed, n_seed, out);
     note_launch();
     return AGNPY_OK;
 }

@@ -7,7 +7,7 @@ from . import _core, _lib, spectra
 from .grids import as_grid, gamma_e_to_integrate, integrator_code
 from .units import strip, wrap
 
-__all__ = ["Synchrotron"]
+__all__ = ["Synchrotron", "ProtonSynchrotron"]
 
 
 def _blob_models(z, d_L, delta_D, B, R_b, ne_par):
@@ -59,6 +59,14 @@ class Synchrotron:
                                    integrator_code(integrator))
         return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
 
+    def electron_energy_loss_rate(self, gamma):
+        """synchrotron.py:93-99: 4/3 sigma_T c U_B gamma^2 [erg s-1] (closed form, host)"""
+        from . import constants as const
+        B = strip(self.blob.B, "G", "B")
+        U_B = B**2 / (8 * np.pi)
+        return wrap((4 / 3) * const.sigma_T * const.c * U_B * np.asarray(gamma, dtype=np.float64) ** 2,
+                    "erg s-1")
+
     def sed_flux(self, nu):
         """synchrotron.py:229-244"""
         b = self.blob
@@ -68,6 +76,42 @@ class Synchrotron:
 
     def sed_luminosity(self, nu):
         """synchrotron.py:259-265"""
+        d_L = strip(self.blob.d_L, "cm", "d_L")
+        return wrap(4 * np.pi * d_L**2 * strip(self.sed_flux(nu), "erg cm-2 s-1"), "erg s-1")
+
+    def sed_peak_flux(self, nu):
+        return self.sed_flux(nu).max()
+
+    def sed_peak_nu(self, nu):
+        return nu[self.sed_flux(nu).argmax()]
+
+
+class ProtonSynchrotron:
+    """synchrotron/proton_synchrotron.py:14-187: synchrotron radiation of the protons of a blob
+    (`blob.n_p`, `blob.gamma_p`); the reference has no self-absorption for protons."""
+
+    def __init__(self, blob, integrator=np.trapezoid):
+        self.blob = blob
+        self.integrator = integrator
+
+    @staticmethod
+    def evaluate_sed_flux(nu, z, d_L, delta_D, B, R_b, n_p, *args, integrator=np.trapezoid,
+                          gamma=gamma_e_to_integrate):
+        """proton_synchrotron.py:69-151"""
+        nu_hz = strip(nu, "Hz", "nu")
+        kind, par, gamma, ne_t, _ = _ne_setup(n_p, args, gamma, False)
+        models = _blob_models(z, d_L, delta_D, B, R_b, par)
+        sed = _core.proton_synch_sed_host(models, kind, np.ravel(nu_hz), gamma, ne_t,
+                                          integrator_code(integrator))
+        return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
+
+    def sed_flux(self, nu):
+        """proton_synchrotron.py:153-167"""
+        b = self.blob
+        return self.evaluate_sed_flux(nu, b.z, b.d_L, b.delta_D, b.B, b.R_b, b.n_p,
+                                      *b.n_p.parameters, integrator=self.integrator, gamma=b.gamma_p)
+
+    def sed_luminosity(self, nu):
         d_L = strip(self.blob.d_L, "cm", "d_L")
         return wrap(4 * np.pi * d_L**2 * strip(self.sed_flux(nu), "erg cm-2 s-1"), "erg s-1")
 

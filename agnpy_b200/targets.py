@@ -133,12 +133,19 @@ class Blob:
     """emission_regions/blob.py:61-151; d_L must be given (the reference derives it from z
     with astropy's cosmology)."""
 
-    def __init__(self, R_b, z, d_L, delta_D, Gamma, B, n_e, gamma_e_size=200):
+    def __init__(self, R_b, z, d_L, delta_D, Gamma, B, n_e, gamma_e_size=200, n_p=None,
+                 gamma_p_size=200):
         if delta_D <= 0:
             raise ValueError("delta_D must be a positive number")
         self.R_b, self.z, self.d_L, self.delta_D, self.Gamma, self.B = R_b, z, d_L, delta_D, Gamma, B
-        self.n_e = n_e
-        self.gamma_e_size = gamma_e_size
+        self.n_e, self.n_p = n_e, n_p
+        self.gamma_e_size, self.gamma_p_size = gamma_e_size, gamma_p_size
+
+    @property
+    def gamma_p(self):
+        """blob.py:153-163"""
+        return np.logspace(np.log10(self.n_p.gamma_min), np.log10(self.n_p.gamma_max),
+                           self.gamma_p_size)
 
     @property
     def Beta(self):

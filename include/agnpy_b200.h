@@ -118,6 +118,16 @@ int agnpy_b200_synch_sed_host(int n_models, const agnpy_model_t* models, int ne_
                               const double* ne_table, const double* ssa_table, int ssa,
                               int integ, double* sed, double* tau_ssa);
 
+/* proton synchrotron: replaces ProtonSynchrotron.evaluate_sed_flux
+ *                    agnpy/synchrotron/proton_synchrotron.py:69-151 (no SSA in the reference);
+ * ne_* describe the proton distribution n_p, `B`/`R_b` as above. */
+int agnpy_b200_proton_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
+                                const double* nu, int n_nu, const double* gamma, int n_gamma,
+                                const double* ne_table, int integ, double* sed, void* stream);
+int agnpy_b200_proton_synch_sed_host(int n_models, const agnpy_model_t* models, int ne_kind,
+                                     const double* nu, int n_nu, const double* gamma, int n_gamma,
+                                     const double* ne_table, int integ, double* sed);
+
 /* ---- synchrotron self-Compton -----------------------------------------------------------
  * replaces SynchrotronSelfCompton.evaluate_sed_flux
  *          agnpy/compton/synchrotron_self_compton.py:73-158 (+ kernels.py:9-33, blob.py:395-404)
@@ -130,6 +140,20 @@ int agnpy_b200_ssc_sed_host(int n_models, const agnpy_model_t* models, int ne_ki
                             const double* nu, int n_nu, const double* nu_seed, int n_seed,
                             const double* gamma, int n_gamma, const double* ne_table,
                             const double* ssa_table, int ssa, int integ, double* sed);
+
+/* SSC energy-loss rate of the electrons [erg s-1] at the Lorentz factors gamma_eval (Klein-Nishina
+ * corrected): replaces SynchrotronSelfCompton.electron_energy_loss_rate
+ *             agnpy/compton/synchrotron_self_compton.py:43-71
+ * (seed spectrum: synchrotron without SSA on nu_seed, integrated over `gamma` with np.trapz).
+ * out is [n_models][n_eval]. */
+int agnpy_b200_ssc_loss_rate(int n_models, const agnpy_model_t* models, int ne_kind,
+                             const double* gamma_eval, int n_eval, const double* nu_seed, int n_seed,
+                             const double* gamma, int n_gamma, const double* ne_table, double* out,
+                             void* stream);
+int agnpy_b200_ssc_loss_rate_host(int n_models, const agnpy_model_t* models, int ne_kind,
+                                  const double* gamma_eval, int n_eval, const double* nu_seed,
+                                  int n_seed, const double* gamma, int n_gamma,
+                                  const double* ne_table, double* out);
 
 /* ---- external Compton ---------------------------------------------------------------------
  * replaces ExternalCompton.evaluate_sed_flux_{iso_mono,ps_behind_jet,ss_disk,blr,dt}

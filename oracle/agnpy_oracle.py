@@ -953,3 +953,43 @@ def tau_on_synchrotron(nu, z, d_L, delta_D, B, R_b, ne_kind, ne_args, gamma, nu_
     _epsilon, _epsilon1 = broadcast_axes(epsilon, epsilon1)
     _s = _epsilon * _epsilon1 / 2
     return 2 * R_b * trapz(n_synch[..., np.newaxis] * sigma_gg(_s), epsilon, axis=0)
+
+
+# --------------------------------------------------------------------------
+# proton synchrotron and the SSC energy-loss rate
+# --------------------------------------------------------------------------
+MPC2 = M_P * C_LIGHT**2  # conversion.py:7
+
+
+def proton_synch_sed_flux(nu, z, d_L, delta_D, B, R_b, np_kind, np_args, integrator="trapz",
+                          gamma=None):
+    """synchrotron/proton_synchrotron.py:69-151 (epsilon in units of m_p c^2, no SSA)"""
+    integ = _integrator(integrator)
+    gamma = default_gamma() if gamma is None else gamma
+    gmin, gmax = _gamma_bounds(np_kind, np_args)
+    gamma = snap_boundaries(gamma, gmin, gmax)
+    epsilon = (1 + z) * (H_PLANCK * np.asarray(nu, dtype=np.float64) / MPC2) / delta_D
+    _gamma, _epsilon = broadcast_axes(gamma, epsilon)
+    V_b = 4 / 3 * np.pi * np.power(R_b, 3)
+    N_p = V_b * ne_evaluate(np_kind, _gamma, *np_args)
+    integrand = N_p * single_particle_synch_power(B, _epsilon, _gamma, mass=M_P)
+    emissivity = integ(integrand, gamma, axis=0)
+    prefactor = np.power(delta_D, 4) / (4 * np.pi * np.power(d_L, 2))
+    return prefactor * epsilon * emissivity
+
+
+def ssc_electron_energy_loss_rate(gamma_eval, z, d_L, delta_D, B, R_b, ne_kind, ne_args,
+                                  nu_seed=None, gamma=None):
+    """compton/synchrotron_self_compton.py:43-71"""
+    nu_seed = default_nu_seed() if nu_seed is None else nu_seed
+    gamma = default_gamma() if gamma is None else gamma
+    gamma_eval = np.asarray(gamma_eval, dtype=np.float64)
+    epsilon = nu_to_epsilon_prime(nu_seed, z, delta_D)
+    sed = synch_sed_flux(nu_seed, z, d_L, delta_D, B, R_b, ne_kind, ne_args, gamma=gamma)
+    u_epsilon = u_ph_synch_diff(R_b, d_L, delta_D, epsilon, sed)
+    _gamma, _epsilon = broadcast_axes(gamma_eval, epsilon)
+    b = 4 * _gamma * _epsilon
+    with np.errstate(all="ignore"):
+        f_KN = np.where(b < 1e4, 1 / (1 + b) ** 1.5, (9 / (2 * b**2)) * (clipped_log(b) - 11 / 6))
+    F_KN = trapz(f_KN * u_epsilon, epsilon, axis=1)
+    return (4 / 3) * SIGMA_T * C_LIGHT * F_KN * gamma_eval**2

@@ -420,3 +420,38 @@ def test_tau_on_synchrotron(kind):
     got2 = ab.Absorption(blob).tau_on_synchrotron(blob, nu * u.Hz, nu_s_size=120, delta_margin_low=1e-3)
     ref2 = orc.tau_on_synchrotron(nu, 0.5, 1e28, 20, 0.5, 1e16, kind, args, blob.gamma_e, 120, 1e-3)
     assert_parity(got2, ref2, rtol=1e-6, what=f"tau on synchrotron {kind} (120, 1e-3)")
+
+
+# ---------------------------------------------------------------------------------------------
+# proton synchrotron, SSC energy-loss rate
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("integ", ["trapz", "trapz_loglog"])
+def test_proton_synchrotron(integ):
+    """synchrotron/proton_synchrotron.py:69-151; blob of synchrotron/tests/test_proton_synchrotron.py"""
+    from agnpy_b200 import targets
+    args = (1e-4, 2.2, 1.0, 1e9 / 0.938)          # proton power law, k p gamma_min gamma_max
+    n_p = spectra.PowerLaw(*q_args(args))
+    blob = targets.Blob(1e16 * u.cm, 0.5, 1e28 * u.cm, 20, 20, 10 * u.G, spectra.PowerLaw(), n_p=n_p)
+    nu = np.logspace(10, 30, 60)
+    integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
+    got = ab.ProtonSynchrotron(blob, integrator=integrator).sed_flux(nu * u.Hz)
+    ref = orc.proton_synch_sed_flux(nu, 0.5, 1e28, 20, 10.0, 1e16, "PowerLaw", args, integrator=integ,
+                                    gamma=blob.gamma_p)
+    assert_parity(got.value, ref, what=f"proton synchrotron {integ}")
+
+
+def test_ssc_energy_loss_rate():
+    """compton/synchrotron_self_compton.py:43-71, the integral inside every TimeEvolution step"""
+    from agnpy_b200 import targets
+    c = cases.case_c1()
+    ne = ne_obj(c["ne_kind"], q_args(c["ne_args"]))
+    blob = targets.Blob(c["R_b"] * u.cm, c["z"], c["d_L"] * u.cm, c["delta_D"], 10, c["B"] * u.G, ne)
+    gamma = np.logspace(0.5, 8.5, 77)
+    got = ab.SynchrotronSelfCompton(blob).electron_energy_loss_rate(gamma)
+    ref = orc.ssc_electron_energy_loss_rate(gamma, c["z"], c["d_L"], c["delta_D"], c["B"], c["R_b"],
+                                            c["ne_kind"], c["ne_args"])
+    assert got.unit == u.Unit("erg s-1")
+    assert_parity(got.value, ref, what="ssc loss rate")
+    thomson = ab.Synchrotron(blob).electron_energy_loss_rate(gamma)
+    U_B = c["B"] ** 2 / (8 * np.pi)
+    np.testing.assert_allclose(thomson.value, 4 / 3 * orc.SIGMA_T * orc.C_LIGHT * U_B * gamma**2, rtol=1e-14)
