@@ -13,6 +13,9 @@ constexpr size_t kChunkBytes = (size_t)1 << 30;  // scratch budget per batch chu
 
 static bool bad_kind(int k) { return k < AGNPY_NE_POWERLAW || k > AGNPY_NE_TABLE; }
 static bool bad_integ(int i) { return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_PREFIX; }
+static const double* row_at(const double* table, int m0, int n_gamma) {
+    return table ? table + (size_t)m0 * n_gamma : nullptr;  // tables are [n_models][n_gamma]
+}
 static int plain_integ(int i) { return i == AGNPY_INTEG_TRAPZ_PREFIX ? AGNPY_INTEG_TRAPZ : i; }
 
 static int chunk_models(size_t bytes_per_model, int n_models) {
@@ -71,8 +74,8 @@ int agnpy_b200_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         return fail(AGNPY_ERR_ARG, "synch_sed: bad sizes or null pointer");
     if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "synch_sed: bad ne_kind/integ");
     if (n_nu > 65535) return fail(AGNPY_ERR_ARG, "synch_sed: n_nu > 65535");
-    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table || (ssa && !ssa_table)))
-        return fail(AGNPY_ERR_ARG, "synch_sed: AGNPY_NE_TABLE needs n_models == 1 and tables");
+    if (ne_kind == AGNPY_NE_TABLE && (!ne_table || (ssa && !ssa_table)))
+        return fail(AGNPY_ERR_ARG, "synch_sed: AGNPY_NE_TABLE needs n_e (and SSA) tables");
     integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = 3 * (size_t)n_gamma * sizeof(double);
@@ -81,7 +84,8 @@ int agnpy_b200_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
     if (!tab) return fail(AGNPY_ERR_NOMEM, "synch_sed: workspace");
     for (int m0 = 0; m0 < n_models; m0 += chunk) {
         int nm = std::min(chunk, n_models - m0);
-        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, ssa_table, 0, tab, stream);
+        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, row_at(ne_table, m0, n_gamma),
+                          row_at(ssa_table, m0, n_gamma), 0, tab, stream);
         timing_begin(stream);
         int rc_s = launch_synch(models + m0, nm, nu, n_nu, tab, n_gamma, ssa, integ, 0,
                                 sed + (size_t)m0 * n_nu,
@@ -103,8 +107,8 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         return fail(AGNPY_ERR_ARG, "ssc_sed: bad sizes or null pointer");
     if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "ssc_sed: bad ne_kind/integ");
     if (n_nu > 65535 || n_seed > 65535) return fail(AGNPY_ERR_ARG, "ssc_sed: n_nu/n_seed > 65535");
-    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table || (ssa && !ssa_table)))
-        return fail(AGNPY_ERR_ARG, "ssc_sed: AGNPY_NE_TABLE needs n_models == 1 and tables");
+    if (ne_kind == AGNPY_NE_TABLE && (!ne_table || (ssa && !ssa_table)))
+        return fail(AGNPY_ERR_ARG, "ssc_sed: AGNPY_NE_TABLE needs n_e (and SSA) tables");
     integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = (3 * (size_t)n_gamma + 2 * (size_t)n_seed) * sizeof(double);
@@ -116,7 +120,8 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         double* tab = ws;
         double* U = tab + (size_t)nm * 3 * n_gamma;
         double* es = U + (size_t)nm * n_seed;
-        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, ssa_table, 0, tab, stream);
+        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, row_at(ne_table, m0, n_gamma),
+                          row_at(ssa_table, m0, n_gamma), 0, tab, stream);
         // seed synchrotron spectrum at nu_seed (synchrotron_self_compton.py:129-142)
         if (int rc = launch_synch(models + m0, nm, nu_seed, n_seed, tab, n_gamma, ssa, integ, 1, U,
                                   nullptr, es, stream))
@@ -139,8 +144,8 @@ int agnpy_b200_proton_synch_sed(int n_models, const agnpy_model_t* models, int n
         return fail(AGNPY_ERR_ARG, "proton_synch_sed: bad sizes or null pointer");
     if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "proton_synch_sed: bad ne_kind/integ");
     if (n_nu > 65535) return fail(AGNPY_ERR_ARG, "proton_synch_sed: n_nu > 65535");
-    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table))
-        return fail(AGNPY_ERR_ARG, "proton_synch_sed: AGNPY_NE_TABLE needs n_models == 1 and a table");
+    if (ne_kind == AGNPY_NE_TABLE && (!ne_table))
+        return fail(AGNPY_ERR_ARG, "proton_synch_sed: AGNPY_NE_TABLE needs an n_e table");
     integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = 3 * (size_t)n_gamma * sizeof(double);
@@ -149,7 +154,8 @@ int agnpy_b200_proton_synch_sed(int n_models, const agnpy_model_t* models, int n
     if (!tab) return fail(AGNPY_ERR_NOMEM, "proton_synch_sed: workspace");
     for (int m0 = 0; m0 < n_models; m0 += chunk) {
         int nm = std::min(chunk, n_models - m0);
-        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, nullptr, 0, tab, stream);
+        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, row_at(ne_table, m0, n_gamma), nullptr, 0,
+                          tab, stream);
         timing_begin(stream);
         int rc = launch_synch(models + m0, nm, nu, n_nu, tab, n_gamma, 0, integ, 0,
                               sed + (size_t)m0 * n_nu, nullptr, nullptr, stream, 0, 1);
@@ -170,8 +176,8 @@ int agnpy_b200_ssc_loss_rate(int n_models, const agnpy_model_t* models, int ne_k
         return fail(AGNPY_ERR_ARG, "ssc_loss_rate: bad sizes or null pointer");
     if (bad_kind(ne_kind)) return fail(AGNPY_ERR_ARG, "ssc_loss_rate: bad ne_kind");
     if (n_eval > 65535 || n_seed > 65535) return fail(AGNPY_ERR_ARG, "ssc_loss_rate: grid too large");
-    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table))
-        return fail(AGNPY_ERR_ARG, "ssc_loss_rate: AGNPY_NE_TABLE needs n_models == 1 and a table");
+    if (ne_kind == AGNPY_NE_TABLE && (!ne_table))
+        return fail(AGNPY_ERR_ARG, "ssc_loss_rate: AGNPY_NE_TABLE needs an n_e table");
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = (3 * (size_t)n_gamma + 2 * (size_t)n_seed) * sizeof(double);
     int chunk = chunk_models(per, n_models);
@@ -182,7 +188,8 @@ int agnpy_b200_ssc_loss_rate(int n_models, const agnpy_model_t* models, int ne_k
         double* tab = ws;
         double* U = tab + (size_t)nm * 3 * n_gamma;
         double* es = U + (size_t)nm * n_seed;
-        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, ne_table, nullptr, 0, tab, stream);
+        launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, row_at(ne_table, m0, n_gamma), nullptr, 0,
+                          tab, stream);
         if (int rc = launch_synch(models + m0, nm, nu_seed, n_seed, tab, n_gamma, 0, AGNPY_INTEG_TRAPZ, 1,
                                   U, nullptr, es, stream))
             return rc;
@@ -208,8 +215,8 @@ int agnpy_b200_ec_sed(int variant, int n_models, const agnpy_model_t* models, in
     if (need_phi && (!phi || n_phi < 2)) return fail(AGNPY_ERR_ARG, "ec_sed: phi grid required");
     if (need_mu_grid && !mu) return fail(AGNPY_ERR_ARG, "ec_sed: mu grid required");
     if (need_mu_size && n_mu < 2) return fail(AGNPY_ERR_ARG, "ec_sed: n_mu < 2");
-    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table))
-        return fail(AGNPY_ERR_ARG, "ec_sed: AGNPY_NE_TABLE needs n_models == 1 and a table");
+    if (ne_kind == AGNPY_NE_TABLE && (!ne_table))
+        return fail(AGNPY_ERR_ARG, "ec_sed: AGNPY_NE_TABLE needs an n_e table");
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = ec_workspace_bytes(variant, 1, n_nu, n_gamma, n_mu, n_phi);
     int chunk = chunk_models(per, n_models);
@@ -218,7 +225,8 @@ int agnpy_b200_ec_sed(int variant, int n_models, const agnpy_model_t* models, in
     for (int m0 = 0; m0 < n_models; m0 += chunk) {
         int nm = std::min(chunk, n_models - m0);
         if (int rc = run_ec(variant, models + m0, nm, ne_kind, nu, n_nu, gamma, n_gamma, mu, n_mu,
-                            phi, n_phi, ne_table, integ, sed + (size_t)m0 * n_nu, ws, stream))
+                            phi, n_phi, row_at(ne_table, m0, n_gamma), integ, sed + (size_t)m0 * n_nu, ws,
+                            stream))
             return rc;
     }
     return AGNPY_OK;
@@ -263,8 +271,8 @@ int agnpy_b200_tau_synch(int n_models, const agnpy_model_t* models, int ne_kind,
         return fail(AGNPY_ERR_ARG, "tau_synch: bad sizes or null pointer");
     if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "tau_synch: bad ne_kind/integ");
     if (n_s > 65535 || (n_nu + 3) / 4 > 65535) return fail(AGNPY_ERR_ARG, "tau_synch: grid too large");
-    if (ne_kind == AGNPY_NE_TABLE && (n_models != 1 || !ne_table || !ssa_table))
-        return fail(AGNPY_ERR_ARG, "tau_synch: AGNPY_NE_TABLE needs n_models == 1 and both tables");
+    if (ne_kind == AGNPY_NE_TABLE && (!ne_table || !ssa_table))
+        return fail(AGNPY_ERR_ARG, "tau_synch: AGNPY_NE_TABLE needs both tables");
     integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t per = tau_synch_workspace_bytes(1, n_nu, n_gamma, n_s);
@@ -273,7 +281,8 @@ int agnpy_b200_tau_synch(int n_models, const agnpy_model_t* models, int ne_kind,
     if (!ws) return fail(AGNPY_ERR_NOMEM, "tau_synch: workspace");
     for (int m0 = 0; m0 < n_models; m0 += chunk) {
         int nm = std::min(chunk, n_models - m0);
-        if (int rc = run_tau_synch(models + m0, nm, ne_kind, nu, n_nu, gamma, n_gamma, ne_table, ssa_table,
+        if (int rc = run_tau_synch(models + m0, nm, ne_kind, nu, n_nu, gamma, n_gamma,
+                                   row_at(ne_table, m0, n_gamma), row_at(ssa_table, m0, n_gamma),
                                    n_s, delta_margin_low, integ, tau + (size_t)m0 * n_nu, ws, stream))
             return rc;
     }
@@ -422,8 +431,8 @@ int agnpy_b200_synch_sed_host(int n_models, const agnpy_model_t* models, int ne_
     size_t out_n = (size_t)n_models * n_nu;
     HostIO io;
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
-    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
-    int i_sa = io.in(ssa_table, 8 * (size_t)n_gamma);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma * n_models);
+    int i_sa = io.in(ssa_table, 8 * (size_t)n_gamma * n_models);
     int o_sed = io.out(sed, 8 * out_n), o_tau = io.out(tau_ssa, 8 * out_n);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;
@@ -447,7 +456,7 @@ int agnpy_b200_ssc_sed_host(int n_models, const agnpy_model_t* models, int ne_ki
     HostIO io;
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
     int i_sd = io.in(nu_seed, 8 * (size_t)n_seed), i_g = io.in(gamma, 8 * (size_t)n_gamma);
-    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma), i_sa = io.in(ssa_table, 8 * (size_t)n_gamma);
+    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma * n_models), i_sa = io.in(ssa_table, 8 * (size_t)n_gamma * n_models);
     int o_sed = io.out(sed, 8 * out_n);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;
@@ -471,7 +480,7 @@ int agnpy_b200_ec_sed_host(int variant, int n_models, const agnpy_model_t* model
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
     int i_g = io.in(gamma, 8 * (size_t)n_gamma);
     int i_mu = io.in(mu, 8 * (size_t)(n_mu > 0 ? n_mu : 0)), i_ph = io.in(phi, 8 * (size_t)(n_phi > 0 ? n_phi : 0));
-    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma * n_models);
     int o_sed = io.out(sed, 8 * out_n);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;
@@ -534,8 +543,8 @@ int agnpy_b200_tau_synch_host(int n_models, const agnpy_model_t* models, int ne_
     size_t out_n = (size_t)n_models * n_nu;
     HostIO io;
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
-    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
-    int i_sa = io.in(ssa_table, 8 * (size_t)n_gamma);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma * n_models);
+    int i_sa = io.in(ssa_table, 8 * (size_t)n_gamma * n_models);
     int o_tau = io.out(tau, 8 * out_n);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;
@@ -555,7 +564,7 @@ int agnpy_b200_proton_synch_sed_host(int n_models, const agnpy_model_t* models, 
         return fail(AGNPY_ERR_ARG, "proton_synch_sed_host: bad sizes or null pointer");
     HostIO io;
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
-    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int i_g = io.in(gamma, 8 * (size_t)n_gamma), i_ne = io.in(ne_table, 8 * (size_t)n_gamma * n_models);
     int o_sed = io.out(sed, 8 * (size_t)n_models * n_nu);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;
@@ -577,7 +586,7 @@ int agnpy_b200_ssc_loss_rate_host(int n_models, const agnpy_model_t* models, int
     HostIO io;
     int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_ge = io.in(gamma_eval, 8 * (size_t)n_eval);
     int i_sd = io.in(nu_seed, 8 * (size_t)n_seed), i_g = io.in(gamma, 8 * (size_t)n_gamma);
-    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma);
+    int i_ne = io.in(ne_table, 8 * (size_t)n_gamma * n_models);
     int o = io.out(out, 8 * (size_t)n_models * n_eval);
     if (int rc = io.commit()) return rc;
     if (int rc = io.upload()) return rc;

@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(128) ec_tables_kernel(
     const int nB = (n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;
     int bx = blockIdx.x;
     if (bx == 0) {
-        ec_gamma_role(M, ne_kind, gamma, n_gamma, ne_table, integ, gt + (size_t)m * 5 * n_gamma,
+        ec_gamma_role(M, ne_kind, gamma, n_gamma, ne_table ? ne_table + (size_t)m * n_gamma : nullptr,
+                      integ, gt + (size_t)m * 5 * n_gamma,
                       hull + 2 * m, s_hull);
     } else if (bx < 1 + nB) {
         ec_pairs_role(variant, M, mu, n_mu, phi, n_phi, n_pairs, ang + (size_t)m * 5 * n_pairs,

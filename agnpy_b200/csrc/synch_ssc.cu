@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(128) prep_gamma_kernel(
     }
     double ne, ssa = 0.0;
     if (ne_kind == AGNPY_NE_TABLE) {
-        ne = ne_table[k];
-        if (ssa_table) ssa = ssa_table[k];
+        ne = ne_table[(size_t)m * n_gamma + k];  // one table row per model
+        if (ssa_table) ssa = ssa_table[(size_t)m * n_gamma + k];
     } else {
         ne = ne_eval(ne_kind, M.ne, g_eval);
         if (mode == 0) ssa = ne_ssa(ne_kind, M.ne, g_eval);

@@ -107,8 +107,8 @@ int agnpy_b200_fp64_peak(double ms, double* flops_per_s, void* stream);
  * replaces Synchrotron.evaluate_sed_flux   agnpy/synchrotron/synchrotron.py:131-211
  *      and Synchrotron.evaluate_tau_ssa    agnpy/synchrotron/synchrotron.py:101-129
  * sed[m][i] = nu F_nu [erg cm-2 s-1]; tau_ssa (optional, may be NULL) = SSA optical depth.
- * ne_table / ssa_table ([n_gamma], only for AGNPY_NE_TABLE, n_models must be 1): n_e(gamma)
- * [cm-3] and the SSA integrand on the gamma grid. */
+ * ne_table / ssa_table ([n_models][n_gamma], only for AGNPY_NE_TABLE): n_e(gamma) [cm-3] and
+ * the SSA integrand of every model on the (snapped) gamma grid. */
 int agnpy_b200_synch_sed(int n_models, const agnpy_model_t* models, int ne_kind,
                          const double* nu, int n_nu, const double* gamma, int n_gamma,
                          const double* ne_table, const double* ssa_table, int ssa, int integ,
@@ -160,7 +160,7 @@ int agnpy_b200_ssc_loss_rate_host(int n_models, const agnpy_model_t* models, int
  *          agnpy/compton/external_compton.py:63-142,163-240,261-373,398-490,514-600
  * mu/phi: angle grids (mu ignored for PS/DT; for SS_DISK `mu` is NULL and n_mu = mu_size:
  * the zenith grid is built from R_in,R_out,r as targets/targets.py:289-296).
- * ne_table ([n_gamma], AGNPY_NE_TABLE only): n_e evaluated at gamma/delta_D. */
+ * ne_table ([n_models][n_gamma], AGNPY_NE_TABLE only): n_e evaluated at gamma/delta_D. */
 int agnpy_b200_ec_sed(int variant, int n_models, const agnpy_model_t* models, int ne_kind,
                       const double* nu, int n_nu, const double* gamma, int n_gamma,
                       const double* mu, int n_mu, const double* phi, int n_phi,
