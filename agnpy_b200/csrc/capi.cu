@@ -12,11 +12,13 @@ namespace agb {
 constexpr size_t kChunkBytes = (size_t)1 << 30;  // scratch budget per batch chunk
 
 static bool bad_kind(int k) { return k < AGNPY_NE_POWERLAW || k > AGNPY_NE_TABLE; }
-static bool bad_integ(int i) { return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_PREFIX; }
+static bool bad_integ(int i) { return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_FP32; }
 static const double* row_at(const double* table, int m0, int n_gamma) {
     return table ? table + (size_t)m0 * n_gamma : nullptr;  // tables are [n_models][n_gamma]
 }
-static int plain_integ(int i) { return i == AGNPY_INTEG_TRAPZ_PREFIX ? AGNPY_INTEG_TRAPZ : i; }
+static int plain_integ(int i) {
+    return (i == AGNPY_INTEG_TRAPZ_PREFIX || i == AGNPY_INTEG_TRAPZ_FP32) ? AGNPY_INTEG_TRAPZ : i;
+}
 
 static int chunk_models(size_t bytes_per_model, int n_models) {
     size_t c = kChunkBytes / std::max<size_t>(bytes_per_model, 1);

@@ -16,6 +16,13 @@ def trapz_prefix(*args, **kwargs):
         "agnpy_b200.trapz_prefix only selects the device integrator; it is not a host function")
 
 
+def trapz_fp32(*args, **kwargs):
+    """Selector for the opt-in FP32-integrand evaluation of numpy.trapz in the external Compton
+    kernels (AGNPY_INTEG_TRAPZ_FP32): masks and outer sums stay FP64, rtol ~1e-6."""
+    raise NotImplementedError(
+        "agnpy_b200.trapz_fp32 only selects the device integrator; it is not a host function")
+
+
 def trapz_loglog(*args, **kwargs):
     """Selector for the device-side log-log trapezoidal rule (utils/math.py:55-119).
     Pass it as `integrator=`; the integration itself happens inside the CUDA kernels."""
@@ -39,6 +46,8 @@ def integrator_code(integrator):
         return _lib.INTEG_LOGLOG
     if name == "trapz_prefix":
         return _lib.INTEG_TRAPZ_PREFIX
+    if name == "trapz_fp32":
+        return _lib.INTEG_TRAPZ_FP32
     raise ValueError(
         f"unsupported integrator {integrator!r}: use numpy.trapz or trapz_loglog")
 

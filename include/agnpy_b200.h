@@ -46,6 +46,9 @@ extern "C" {
  * points treat it as AGNPY_INTEG_TRAPZ).  Same integral, grid and masks; the gamma sum is
  * re-associated (differences ~1e-15).  Opt-in: see DESIGN.md section 4. */
 #define AGNPY_INTEG_TRAPZ_PREFIX 2
+/* numpy.trapz with the integrand evaluated in FP32 (external Compton only; masks, angle sums and
+ * prefactors stay FP64).  Opt-in reduced precision: rtol ~1e-6 instead of 1e-9. */
+#define AGNPY_INTEG_TRAPZ_FP32 3
 
 /* external-Compton targets: agnpy/compton/external_compton.py */
 #define AGNPY_EC_ISO_MONO 0      /* :63-142   tgt = {epsilon_0, u_0}                              */
