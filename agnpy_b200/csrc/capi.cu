@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/agnpy_b200.h: argument checks, workspace
 // carving, batching of the model axis, and the host-pointer flavours (H2D, run, D2H, sync).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -21,7 +22,12 @@ static int plain_integ(int i) {
 }
 
 static int chunk_models(size_t bytes_per_model, int n_models) {
-    size_t c = kChunkBytes / std::max<size_t>(bytes_per_model, 1);
+    size_t budget = kChunkBytes;
+    if (const char* e = getenv("AGNPY_B200_CHUNK_BYTES")) {  // test knob: force small chunks
+        long long v = atoll(e);
+        if (v > 0) budget = (size_t)v;
+    }
+    size_t c = budget / std::max<size_t>(bytes_per_model, 1);
     c = std::max<size_t>(1, std::min<size_t>(c, 65535));
     return (int)std::min<size_t>(c, (size_t)n_models);
 }

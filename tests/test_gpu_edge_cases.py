@@ -186,3 +186,49 @@ def test_units_are_converted_not_assumed():
         c["R_b"] / 100 * u.m, c["L_disk"] / 1e7 * u.W, c["xi_dt"], c["epsilon_dt"], c["R_dt"] / pc * u.pc,
         c["r"] / pc * u.pc, ne[0], ne[1].to("m-3"), *ne[2:], gamma=c["gamma"], phi=c["phi"])
     np.testing.assert_allclose(a.value, b.value, rtol=1e-12)
+
+
+def test_model_axis_chunking(monkeypatch):
+    """the model axis is processed in scratch-limited chunks: force tiny chunks and check that
+    every process gives the same rows as one unchunked call"""
+    import bench
+    from agnpy_b200.batch import SedBatch
+    from agnpy_b200 import _core
+    g = bench.grids()
+    nu = g["nu"][::10]
+    models = bench.synthetic_models(11)
+    kw = dict(gamma=g["gamma"][::2], mu=g["mu"][::5], phi=g["phi"][::5])
+    tmodels = _lib.make_models(11)
+    for i in range(11):
+        _core.model_row(tmodels, i, z=0.3, mu_s=1.0, tgt=[cases.L_DISK, 0.024, cases.EPS_LINE, 1e17, 1e16 * (1 + i)])
+    ref = {}
+    for proc in ("ec_blr", "ssc", "synch", "tau_blr"):
+        m = tmodels if proc == "tau_blr" else models
+        ref[proc] = SedBatch(proc, nu if proc != "tau_blr" else cases.case_tau(12)["nu"], "BrokenPowerLaw", **kw)(m)
+    monkeypatch.setenv("AGNPY_B200_CHUNK_BYTES", "300000")      # 1-3 models per chunk
+    for proc in ("ec_blr", "ssc", "synch", "tau_blr"):
+        m = tmodels if proc == "tau_blr" else models
+        got = SedBatch(proc, nu if proc != "tau_blr" else cases.case_tau(12)["nu"], "BrokenPowerLaw", **kw)(m)
+        np.testing.assert_array_equal(got, ref[proc])
+        assert np.count_nonzero(got) > 0
+
+
+@pytest.mark.parametrize("grid", ["fine", "linear", "coarse"])
+def test_unusual_gamma_grids(grid):
+    """very fine grids put many gamma points inside the mask guard bands (exact fall-back path);
+    linear and very coarse grids change the search geometry"""
+    gamma = {"fine": np.logspace(2, 5, 1500), "linear": np.linspace(30.0, 3e5, 400),
+             "coarse": np.logspace(1, 9, 12)}[grid]
+    c = cases.case_c2(n_nu=14, r=2e17, n_mu=21, n_phi=11)
+    c["gamma"] = gamma
+    for integ, integrator in (("trapz", np.trapezoid), ("trapz_loglog", ab.trapz_loglog), ("trapz", ab.trapz_prefix)):
+        assert_parity(blr_call(c, integrator=integrator), cases.ORACLE_EC["blr"](c, integ), what=f"ec {grid} {integ}")
+    c1 = cases.case_c1(n_nu=16)
+    g1 = {"fine": np.logspace(1, 4, 1200), "linear": np.linspace(10.0, 1e5, 300), "coarse": np.logspace(1, 6, 9)}[grid]
+    for integ, integrator in (("trapz", np.trapezoid), ("trapz_loglog", ab.trapz_loglog)):
+        got = ab.SynchrotronSelfCompton.evaluate_sed_flux(
+            c1["nu"] * u.Hz, c1["z"], c1["d_L"] * u.cm, c1["delta_D"], c1["B"] * u.G, c1["R_b"] * u.cm,
+            ne_obj(c1["ne_kind"], c1["ne_args"]), *q_args(c1["ne_args"]), integrator=integrator, gamma=g1)
+        ref = orc.ssc_sed_flux(c1["nu"], c1["z"], c1["d_L"], c1["delta_D"], c1["B"], c1["R_b"], c1["ne_kind"],
+                               c1["ne_args"], integrator=integ, gamma=g1)
+        assert_parity(got.value, ref, what=f"ssc {grid} {integ}")
