@@ -229,6 +229,9 @@ __global__ void __launch_bounds__(256) ssc_kernel(
     double* s_idl = s_qlo2 + n_gamma;  // loglog only: 1/(ln g_k - ln g_k+1)
     double* s_lr = s_idl + n_gamma;    // loglog only: ln(g_k+1/g_k)
     double* s_Y = s_lr + n_gamma;      // loglog only: [n_seed] gamma-integrals
+    // trapz only: the same tables interleaved as double2 {f,h} {ln h,c1} {q_lo,q_lo2}; placed at
+    // an even double offset so the 16-byte loads are aligned (dynamic smem is 16-byte aligned)
+    double* s_pack = sh + ((7 * n_gamma + 1) & ~1);
     for (int k = threadIdx.x; k < n_gamma; k += blockDim.x) {
         double g = gs[k];
         double f = Ne[k] / (g * g);
@@ -244,6 +247,14 @@ __global__ void __launch_bounds__(256) ssc_kernel(
         s_c1[k] = 1.0 + 0.5 * (v * v) / (1.0 + v);
         s_qlo[k] = qmin * (1.0 + kGuard);
         s_qlo2[k] = qmin * (1.0 - kGuard);
+        if (INTEG == AGNPY_INTEG_TRAPZ) {
+            s_pack[2 * k] = f;
+            s_pack[2 * k + 1] = h;
+            s_pack[2 * n_gamma + 2 * k] = log(h);
+            s_pack[2 * n_gamma + 2 * k + 1] = 1.0 + 0.5 * (v * v) / (1.0 + v);
+            s_pack[4 * n_gamma + 2 * k] = qmin * (1.0 + kGuard);
+            s_pack[4 * n_gamma + 2 * k + 1] = qmin * (1.0 - kGuard);
+        }
         if (INTEG == AGNPY_INTEG_LOGLOG && k < n_gamma - 1) {
             double gu = gs[k + 1];
             s_idl[k] = 1.0 / (clipped_log(g) - clipped_log(gu));
@@ -260,18 +271,24 @@ __global__ void __launch_bounds__(256) ssc_kernel(
         const double lie = -log(eps);
         double acc = 0.0;
         if (INTEG == AGNPY_INTEG_TRAPZ) {
+            // hot loop reads {f, h}, {ln h, c1}, {q_lo, q_lo2} as three 16-byte broadcasts
+            const double2* p_fh = reinterpret_cast<const double2*>(s_pack);
+            const double2* p_lc = p_fh + n_gamma;
+            const double2* p_qq = p_lc + n_gamma;
             for (int k = 0; k < n_gamma; ++k) {
-                double f = s_f[k];
-                if (f == 0.0) continue;  // block-uniform: outside the electron distribution
-                double q = s_h[k] * ie;
-                if (q >= s_qlo[k] && q <= 1.0 - kGuard) {
-                    double lq = s_lh[k] + lie;
-                    double F = fma(q + q, lq, (1.0 - q) * fma(2.0, q, s_c1[k]));
-                    acc = fma(f, F, acc);
-                } else if (q >= s_qlo2[k] && q <= 1.0 + kGuard) {
+                double2 fh = p_fh[k];
+                if (fh.x == 0.0) continue;  // block-uniform: outside the electron distribution
+                double q = fh.y * ie;
+                double2 qq = p_qq[k];
+                if (q >= qq.x && q <= 1.0 - kGuard) {
+                    double2 lc = p_lc[k];
+                    double lq = lc.x + lie;
+                    double F = fma(q + q, lq, (1.0 - q) * fma(2.0, q, lc.y));
+                    acc = fma(fh.x, F, acc);
+                } else if (q >= qq.y && q <= 1.0 + kGuard) {
                     bool in;
                     double F = Fc_exact(s_g[k], eps, eps_s, in);
-                    if (in) acc = fma(f, F, acc);
+                    if (in) acc = fma(fh.x, F, acc);
                 }
             }
             double w = trapz_weight(es, j, n_seed);
@@ -323,7 +340,7 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
                const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,
                int n_seed, int integ, double* out, cudaStream_t stream) {
     dim3 grid(n_nu, n_models);
-    size_t smem = (integ == AGNPY_INTEG_LOGLOG ? 9 * (size_t)n_gamma + n_seed : 7 * (size_t)n_gamma) *
+    size_t smem = (integ == AGNPY_INTEG_LOGLOG ? 9 * (size_t)n_gamma + n_seed : 13 * (size_t)n_gamma + 2) *
                   sizeof(double);
     if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for ssc kernel");
     if (integ == AGNPY_INTEG_TRAPZ) {
