@@ -66,12 +66,11 @@ __device__ __forceinline__ double disk_epsilon(double L_disk, double M_BH, doubl
 //                        ang[m][3][j] = W_j        np.trapz weights x geometric factor
 //                        ang[m][4][j] = c_j = 2 eps_j (1 - cos psi_j)   (mask threshold on G)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ec_pairs_role(
+__device__ __forceinline__ void ec_pair_values(
     int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_mu,
-    const double* __restrict__ phi, int n_phi, int n_pairs, double* __restrict__ row, int j) {
-    if (j >= n_pairs) return;
+    const double* __restrict__ phi, int n_phi, int j, double& eps, double& omc, double& W) {
     const double* t = M.tgt;
-    double eps, cpsi, W;
+    double cpsi;
     if (variant == AGNPY_EC_PS_BEHIND_JET) {  // external_compton.py:226: mu = 1, phi = 0
         eps = t[0];
         cpsi = cos_psi(M.mu_s, 1.0, 0.0);
@@ -114,12 +113,65 @@ __device__ __forceinline__ void ec_pairs_role(
             W = wmu * wphi * (phi_disk / (eps * eps) / mu_i / pow(mm2, 3.0 / 2.0));
         }
     }
-    double omc = 1.0 - cpsi;
-    row[j] = eps;
-    row[n_pairs + j] = omc;
-    row[2 * n_pairs + j] = 1.0 / (eps * omc);
-    row[3 * n_pairs + j] = W;
-    row[4 * n_pairs + j] = 2.0 * (eps * omc);
+    omc = 1.0 - cpsi;
+}
+
+// unsorted pair values of one model: raw[m][0][j] = eps_j, [1][j] = 1 - cos psi_j, [2][j] = W_j
+__device__ __forceinline__ void ec_pairs_role(
+    int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_mu,
+    const double* __restrict__ phi, int n_phi, int n_pairs, double* __restrict__ raw, int j) {
+    if (j >= n_pairs) return;
+    double eps, omc, W;
+    ec_pair_values(variant, M, mu, n_mu, phi, n_phi, j, eps, omc, W);
+    raw[j] = eps;
+    raw[n_pairs + j] = omc;
+    raw[2 * n_pairs + j] = W;
+}
+
+// One 1024-thread block takes one segment of kPairSeg consecutive pairs, one pair per thread,
+// and stores it sorted by descending c_j (pairs that can never contribute, c_j <= 0 or NaN,
+// last): consecutive table entries then have nearly equal first-unmasked gamma indices, which
+// is what lets a warp of the main kernel share one short index window.  The order of the
+// (mu,phi) sum is free (it is a plain weighted sum).  The sort is a bitonic network on one
+// packed 64-bit key per thread -- high word of c_j, then the pair index, so it is a total,
+// deterministic order -- exchanged by warp shuffles below stride 32 and through shared memory
+// above.
+constexpr int kPairSeg = 1024;
+__device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ raw, int n_pairs,
+                                                   double* __restrict__ row, int seg,
+                                                   unsigned long long* s_x) {
+    const int t = threadIdx.x, j0 = seg * kPairSeg, cnt = min(kPairSeg, n_pairs - j0);
+    unsigned long long v = 0ull;  // padding sorts behind every real pair
+    if (t < cnt) {
+        const double c = 2.0 * (raw[j0 + t] * raw[n_pairs + j0 + t]);
+        const unsigned hi = (c > 0.0) ? (unsigned)(__double_as_longlong(c) >> 32) : 0u;
+        v = ((unsigned long long)hi << 32) | (unsigned)(~(unsigned)t);
+    }
+    for (int size = 2; size <= kPairSeg; size <<= 1) {
+        const bool desc = (t & size) == 0;
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            unsigned long long other;
+            if (stride < 32) {
+                other = __shfl_xor_sync(0xffffffffu, v, stride);
+            } else {
+                __syncthreads();
+                s_x[t] = v;
+                __syncthreads();
+                other = s_x[t ^ stride];
+            }
+            const bool keep_max = ((t & stride) == 0) == desc;
+            v = keep_max ? max(v, other) : min(v, other);
+        }
+    }
+    if (t < cnt) {
+        const int src = j0 + (int)(~(unsigned)(v & 0xffffffffull)), j = j0 + t;
+        const double e = raw[src], o = raw[n_pairs + src], w = raw[2 * n_pairs + src];
+        row[j] = e;
+        row[n_pairs + j] = o;
+        row[2 * n_pairs + j] = 1.0 / (e * o);
+        row[3 * n_pairs + j] = w;
+        row[4 * n_pairs + j] = 2.0 * (e * o);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -181,16 +233,17 @@ __device__ __forceinline__ void ec_nu_role(const agnpy_model_t& M, const double*
     nt_row[(size_t)i * n_gamma + k] = v;
 }
 
-// One launch builds all three tables; the block role follows from blockIdx.x:
+// First table launch (128 threads); the block role follows from blockIdx.x:
 //   [0, 1)                     gamma tables + hull
-//   [1, 1 + nB)                pair table, 128 pairs per block
-//   [1 + nB, 1 + nB + nC*n_nu) {A, G} table, 128 gammas of one frequency per block
+//   [1, 1 + nB)                unsorted pair values, 128 pairs per block
+//   [1 + nB, 1 + nB + nC*n_nu) {A, G} table, 128 gammas of one frequency per block (not launched
+//                              on the np.trapz path, whose row role computes A and G itself)
 __global__ void __launch_bounds__(128) ec_tables_kernel(
     int variant, const agnpy_model_t* __restrict__ models, int ne_kind,
     const double* __restrict__ nu, int n_nu, const double* __restrict__ gamma, int n_gamma,
     const double* __restrict__ mu, int n_mu, const double* __restrict__ phi, int n_phi,
     const double* __restrict__ ne_table, int integ, int n_pairs, double* __restrict__ gt,
-    int* __restrict__ hull, double* __restrict__ ang, double2* __restrict__ nt) {
+    int* __restrict__ hull, double* __restrict__ raw, double2* __restrict__ nt) {
     __shared__ int s_hull[2];
     const int m = blockIdx.y;
     const agnpy_model_t& M = models[m];
@@ -201,7 +254,7 @@ __global__ void __launch_bounds__(128) ec_tables_kernel(
                       integ, gt + (size_t)m * 5 * n_gamma,
                       hull + 2 * m, s_hull);
     } else if (bx < 1 + nB) {
-        ec_pairs_role(variant, M, mu, n_mu, phi, n_phi, n_pairs, ang + (size_t)m * 5 * n_pairs,
+        ec_pairs_role(variant, M, mu, n_mu, phi, n_phi, n_pairs, raw + (size_t)m * 3 * n_pairs,
                       (bx - 1) * 128 + threadIdx.x);
     } else {
         bx -= 1 + nB;
@@ -376,6 +429,330 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
 #pragma unroll
             for (int jj = 0; jj < J; ++jj)
                 if (c[jj] > 0.0) thread_sum = fma(W[jj], acc[jj], thread_sum);
+        }
+        thread_sum = warp_sum(thread_sum);
+        if ((tid & 31) == 0)
+            part[(((size_t)m * n_nu + i) * S + slice) * W_per_block + (tid >> 5)] = thread_sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// np.trapz main path (v6): the integrand as a polynomial in b, frequency-incremental masks.
+//
+// With the trapz weight folded into wf_k = w_k N_e(gamma_k)/gamma_k^2 the summand of the gamma
+// integral is
+//     wf_k K_k(b) = wf_k (A_k + t (t - 2)),  t = G_k b
+//                 = P_k + Q_k b^2 + R_k b,   P_k = wf_k A_k,  Q_k = wf_k G_k^2,  R_k = -2 wf_k G_k,
+// so each integrand point costs two DFMAs, acc = fma(Q_k, b^2, acc); acc = fma(R_k, b, acc): one
+// warp-uniform operand each, which the register file feeds at 85 % of the FP64 issue rate where
+// the three-register Horner form fma(fma(Q,b,R),b,acc) stops at 67 % (scripts/micro/fp64_mix.cu).
+// The b-independent term sums to SP[k0] = sum_{k >= k0} P_k, a suffix sum per (nu, model); every
+// pair adds SP at its own first unmasked index.  No cancellation is introduced: on the unmasked
+// range 0 < t <= 2, so Q b^2 + R b = wf (t^2 - 2t) lies in [-wf, 0] while P = wf A >= 2 wf.
+//
+// ec_tables2_kernel writes one row per (nu, model): {Q,R}[n] (16-byte pairs), G[n], SP[n+1]
+// and the index range where y = 1 - eps_s/gamma < 1e-8 (G ill-conditioned).
+// ec_main_poly_kernel: grid = (S pair slices, nu chunks, models), 128 threads x J consecutive
+// pairs (phi fastest, so the first unmasked indices of a warp lie close together).  A block keeps
+// its pairs in registers and walks L_nu consecutive frequencies; the row of frequency i+1 streams
+// into the second shared-memory buffer (cp.async) while frequency i is integrated.  The first
+// unmasked index -- first k with G_k <= c, as in the v4 kernel above -- moves up by a few grid
+// points per frequency step (G_k grows with nu), so after the binary search of the first
+// frequency it is advanced by three probes and verified; anything unexpected (descending nu,
+// coarse grids) falls back to the binary search.  Comparisons run on the bit patterns of the
+// positive doubles (integer pipe, not FP64).  The guard band around c (|hi32(G) - hi32(c)| <= 3,
+// i.e. >= 1.4e-6 relative) and the exact re-decision inside it are those of the v4 kernel.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int ec_row_words(int n_gamma) { return (4 * n_gamma + 2 + 1) & ~1; }
+
+// Second table launch (1024 threads); the block role follows from blockIdx.x:
+//   [0, nSeg)            pair table: one sorted segment per block (from the unsorted values)
+//   [nSeg, nSeg + nR)    np.trapz path only: polynomial rows, one warp per (nu, model) row.
+// Row role: lane l owns gamma indices l, l+32, ...: it evaluates y, A, G (kernels.py:61-65 in the
+// operation order of ec_nu_role), writes {Q,R} and G, and the warp builds the suffix sums of
+// P = wf A from the top of the grid down (shuffle scan per group of 32 plus a running carry).
+constexpr int kTab2Threads = 1024;
+__device__ __forceinline__ void ec_poly_row_role(
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
+    const double* __restrict__ gamma, int n_gamma, const double* __restrict__ gt,
+    const int* __restrict__ hull, double* __restrict__ rows, int i, int m) {
+    const int lane = threadIdx.x & 31;
+    if (i >= n_nu) return;
+    const double* g_f = gt + (size_t)m * 5 * n_gamma + n_gamma;
+    double* row = rows + ((size_t)m * n_nu + i) * ec_row_words(n_gamma);
+    double2* r_QR = reinterpret_cast<double2*>(row);
+    double* r_G = row + 2 * n_gamma;
+    double* r_SP = r_G + n_gamma;
+    const int klo = hull[2 * m], khi = hull[2 * m + 1];
+    // EC uses nu_to_epsilon_prime(nu, z) without the Doppler factor (external_compton.py:123)
+    const double eps_s = nu_to_eps(nu[i], models[m].z, 1.0);
+    double carry = 0.0;
+    int ill_lo = n_gamma, ill_hi = 0;
+    for (int base = ((n_gamma - 1) >> 5) << 5; base >= 0; base -= 32) {
+        const int k = base + lane;
+        double P = 0.0;
+        if (k < n_gamma) {
+            const double g = gamma[k];
+            const double y = 1.0 - eps_s / g;
+            const double A = y + 1.0 / y;
+            const double G = (y > 0.0) ? eps_s / ((g * g) * y) : INFINITY;
+            const double wf = g_f[k];
+            const bool live = k >= klo && k <= khi && G < kFmax;
+            const double wG = wf * G;
+            r_QR[k] = make_double2(wG * G, -2.0 * wG);
+            r_G[k] = G;
+            P = live ? wf * A : 0.0;
+            if (A > 1e8) { ill_lo = min(ill_lo, k); ill_hi = max(ill_hi, k + 1); }
+        }
+        double incl = P;  // suffix sum over the lanes of this group
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
+        }
+        if (k < n_gamma) r_SP[k] = incl + carry;
+        carry += __shfl_sync(0xffffffffu, incl, 0);
+    }
+    ill_lo = __reduce_min_sync(0xffffffffu, ill_lo);
+    ill_hi = __reduce_max_sync(0xffffffffu, ill_hi);
+    if (lane == 0) {
+        r_SP[n_gamma] = 0.0;
+        *reinterpret_cast<int2*>(r_SP + n_gamma + 1) = make_int2(ill_lo, ill_hi);
+    }
+}
+
+__global__ void __launch_bounds__(kTab2Threads) ec_tables2_kernel(
+    const double* __restrict__ raw, int n_pairs, int n_seg, double* __restrict__ ang,
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
+    const double* __restrict__ gamma, int n_gamma, const double* __restrict__ gt,
+    const int* __restrict__ hull, double* __restrict__ rows) {
+    __shared__ unsigned long long s_x[kPairSeg];
+    const int m = blockIdx.y;
+    if ((int)blockIdx.x < n_seg) {
+        ec_pairs_sort_role(raw + (size_t)m * 3 * n_pairs, n_pairs, ang + (size_t)m * 5 * n_pairs,
+                           blockIdx.x, s_x);
+    } else {
+        ec_poly_row_role(models, nu, n_nu, gamma, n_gamma, gt, hull, rows,
+                         ((int)blockIdx.x - n_seg) * (kTab2Threads / 32) + (threadIdx.x >> 5), m);
+    }
+}
+
+// 1-D bulk copy (TMA engine) global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                              unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// first k with G_k <= c on the bit patterns (G descending; +inf for gamma <= eps_s)
+__device__ __forceinline__ int ec_search_first_le(const long long* s_Gi, int n_gamma, long long c) {
+    int lo = 0, hi = n_gamma;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_Gi[mid] <= c) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+// move a first-(G_k <= c) index found for a neighbouring frequency to the current table
+__device__ __forceinline__ int ec_search_step(const long long* s_Gi, int n_gamma, long long c, int k) {
+    while (k < n_gamma && s_Gi[k] > c) ++k;
+    while (k > 0 && s_Gi[k - 1] <= c) --k;
+    return k;
+}
+// the reference's own decision (kernels.py:36-40) for one (nu, pair)
+__device__ __noinline__ int ec_first_unmasked_ref(const double* __restrict__ gm, int n_gamma,
+                                                  const double* __restrict__ a_eps,
+                                                  const double* __restrict__ a_omc, int j,
+                                                  double nu_i, double z) {
+    return first_unmasked_exact(gm, n_gamma, a_eps[j], nu_to_eps(nu_i, z, 1.0), a_omc[j]);
+}
+__device__ __forceinline__ long long warp_max_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ long long warp_min_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int J>
+__global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
+    const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma,
+    const double* __restrict__ rows, const double* __restrict__ ang, int n_pairs, int S, int L_nu,
+    double* __restrict__ part) {
+    extern __shared__ __align__(16) double sh[];  // L_nu rows, then L_nu mbarriers
+    const int slice = blockIdx.x, m = blockIdx.z;
+    const int i0 = blockIdx.y * L_nu, i1 = min(i0 + L_nu, n_nu);
+    const int T = blockDim.x, tid = threadIdx.x, W_per_block = T >> 5;
+    const int row_words = ec_row_words(n_gamma);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + (size_t)L_nu * row_words);
+    if (tid == 0) {
+        for (int r = 0; r < i1 - i0; ++r) mbar_init(bars + r, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    const double* g_gm = gt + (size_t)m * 5 * n_gamma;
+    const double* a_eps = ang + (size_t)m * 5 * n_pairs;
+    const double* a_omc = a_eps + n_pairs;
+    const double* a_b = a_omc + n_pairs;
+    const double* a_W = a_b + n_pairs;
+    const double* a_c = a_W + n_pairs;
+    const int klo = hull[2 * m], khi = hull[2 * m + 1];  // non-zero range of n_e
+    const double* g_rows = rows + (size_t)m * n_nu * row_words;
+    const int jbase = (slice * T + tid) * J;
+    if (tid == 0) {  // all rows of this block's frequency chunk, one bulk copy each
+        const unsigned row_bytes = (unsigned)row_words * sizeof(double);
+        for (int r = 0; r < i1 - i0; ++r) {
+            mbar_expect_tx(bars + r, row_bytes);
+            bulk_copy_g2s(sh + (size_t)r * row_words, g_rows + (size_t)(i0 + r) * row_words, row_bytes,
+                          bars + r);
+        }
+    }
+
+    double b[J], b2[J];
+    long long ci[J];  // bits of c (> 0); <= 0 marks a pair that never contributes
+    long long cmax = -1, cmin = LLONG_MAX;  // over the live pairs of the warp
+#pragma unroll
+    for (int jj = 0; jj < J; ++jj) {
+        const int j = jbase + jj;
+        const bool valid = j < n_pairs;
+        b[jj] = valid ? a_b[j] : 0.0;
+        b2[jj] = b[jj] * b[jj];
+        const double c = valid ? a_c[j] : -1.0;
+        ci[jj] = (c > 0.0) ? __double_as_longlong(c) : -1LL;
+        if (ci[jj] > 0) { cmax = max(cmax, ci[jj]); cmin = min(cmin, ci[jj]); }
+    }
+    cmax = warp_max_ll(cmax);
+    cmin = warp_min_ll(cmin);
+    const bool warp_live = cmax > 0 && khi >= 0;
+    int wlo = 0, whi = 0;  // first k with G_k <= cmax / <= cmin for the current frequency
+    for (int i = i0; i < i1; ++i) {
+        // warps run through the chunk independently: the only wait is for row i to have landed
+        mbar_wait(bars + (i - i0), 0);
+        const double* s_row = sh + (size_t)(i - i0) * row_words;
+        const double2* s_QR = reinterpret_cast<const double2*>(s_row);
+        const long long* s_Gi = reinterpret_cast<const long long*>(s_row + 2 * n_gamma);
+        const int* s_Gh = reinterpret_cast<const int*>(s_row + 2 * n_gamma);  // [2k+1] = high word
+        const double* s_SP = s_row + 3 * n_gamma;
+        double thread_sum = 0.0;
+        if (warp_live) {
+            // warp-uniform index window [wlo, whi]: every live pair's first unmasked index lies in it
+            if (i == i0) {
+                wlo = ec_search_first_le(s_Gi, n_gamma, cmax);
+                whi = ec_search_first_le(s_Gi, n_gamma, cmin);
+            } else {
+                wlo = ec_search_step(s_Gi, n_gamma, cmax, wlo);
+                whi = ec_search_step(s_Gi, n_gamma, cmin, whi);
+            }
+            // per pair: lo = wlo + #{k in [wlo, whi) : G_k > c}   (G descending: a prefix count)
+            int lo[J];
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) lo[jj] = wlo;
+            for (int k = wlo; k < whi; ++k) {
+                const long long g = s_Gi[k];
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) lo[jj] += (g > ci[jj]) ? 1 : 0;
+            }
+            // guard band: a neighbour of the index within ~1e-6 of c, an ill-conditioned G in the
+            // window, or a non-finite c -> decide that pair with the reference's own formula
+            const int2 ill = *reinterpret_cast<const int2*>(s_SP + n_gamma + 1);
+            const bool w_ill = max(wlo - 1, 0) < ill.y && min(whi, n_gamma - 1) >= ill.x;
+            unsigned doubt = 0;
+            int tmin = INT_MAX, tmax = 0;  // over this thread's live pairs
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                const int k = lo[jj];
+                const int hc = (int)(ci[jj] >> 32);
+                const int ha = s_Gh[2 * min(k, n_gamma - 1) + 1], hb = s_Gh[2 * max(k - 1, 0) + 1];
+                const bool d = (k < n_gamma && abs(ha - hc) <= 3) || (k > 0 && abs(hb - hc) <= 3) ||
+                               w_ill || hc >= 0x7ff00000;
+                if (ci[jj] > 0) {
+                    if (d) doubt |= 1u << jj;
+                    tmin = min(tmin, k);
+                    tmax = max(tmax, k);
+                } else {
+                    lo[jj] = n_gamma;
+                }
+            }
+            if (doubt) {  // rare
+                tmin = INT_MAX;
+                tmax = 0;
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    if (doubt & (1u << jj))
+                        lo[jj] = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc, jbase + jj, nu[i],
+                                                       models[m].z);
+                    if (ci[jj] > 0) { tmin = min(tmin, lo[jj]); tmax = max(tmax, lo[jj]); }
+                }
+            }
+            double acc[J];
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) acc[jj] = 0.0;
+            const int kbeg = max(__reduce_min_sync(0xffffffffu, tmin), klo);
+            const int kmid = min(max(__reduce_max_sync(0xffffffffu, tmax), kbeg), khi + 1);
+            // phase 1 (a few steps: the pairs of a warp are neighbours in c): lanes join as the
+            // loop passes their first unmasked index
+            for (int k = kbeg; k < kmid; ++k) {
+                const double2 qr = s_QR[k];
+                if (k >= tmax) {
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.x, b2[jj], acc[jj]);
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.y, b[jj], acc[jj]);
+                } else if (k >= tmin) {
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj)
+                        if (k >= lo[jj]) acc[jj] = fma(qr.y, b[jj], fma(qr.x, b2[jj], acc[jj]));
+                }
+            }
+            // phase 2: every live lane is above its gamma_min -> 2 DFMA per integrand point
+            // (the table entry of step k+1 is fetched before the 2J DFMAs of step k issue, so
+            // the shared-memory latency hides behind them even when the warp runs alone)
+            if (kmid <= khi) {
+                double2 qr = s_QR[kmid];
+                for (int k = kmid; k <= khi; ++k) {
+                    const double2 nx = s_QR[min(k + 1, khi)];
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.x, b2[jj], acc[jj]);
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.y, b[jj], acc[jj]);
+                    qr = nx;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                const int ks = max(lo[jj], klo);
+                if (ks <= khi) thread_sum = fma(a_W[jbase + jj], acc[jj] + s_SP[ks], thread_sum);
+            }
         }
         thread_sum = warp_sum(thread_sum);
         if ((tid & 31) == 0)
@@ -699,8 +1076,9 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
 // doubles of scratch per model
 static size_t ec_words(const EcPlan& p, int n_nu, int n_gamma) {
     return 5 * (size_t)n_gamma + 2      // gamma tables + hull (2 ints in one double slot, padded)
-           + 5 * (size_t)p.n_pairs      // pair table
+           + 8 * (size_t)p.n_pairs      // pair table (sorted, 5 columns) + unsorted values (3)
            + 2 * (size_t)n_nu * n_gamma // {A,G}
+           + (size_t)n_nu * ec_row_words(n_gamma)  // polynomial rows (np.trapz path)
            + (size_t)n_nu * p.S * p.W();
 }
 
@@ -732,19 +1110,32 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     const bool fp32 = integ == AGNPY_INTEG_TRAPZ_FP32;
     if (prefix || fp32) integ = AGNPY_INTEG_TRAPZ;  // same tables (trapz weights folded into wf)
     EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
+    const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
+    // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
+    // source variants (<= n_phi pairs) stay on the v4 kernel
+    const bool v5 = integ == AGNPY_INTEG_TRAPZ && !fp32 && !prefix && !use_v4 && p.n_pairs >= 512;
     const size_t M = (size_t)n_models;
     // carve: {A,G} table first (16-byte aligned: ws comes from cudaMalloc), then the rest
     double2* nt = (double2*)ws;
-    double* gt = (double*)(nt + M * n_nu * n_gamma);
+    double* rows = (double*)(nt + M * n_nu * n_gamma);  // 16-byte aligned: even word counts
+    double* gt = rows + M * n_nu * ec_row_words(n_gamma);
     double* ang = gt + M * 5 * n_gamma;
-    double* part = ang + M * 5 * p.n_pairs;
+    double* raw = ang + M * 5 * p.n_pairs;
+    double* part = raw + M * 3 * p.n_pairs;
     int* hull = (int*)(part + M * n_nu * p.S * p.W());
     {
         int nB = (p.n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;
-        dim3 grid(1 + nB + nC * n_nu, n_models);
+        dim3 grid(1 + nB + (v5 ? 0 : nC * n_nu), n_models);
         ec_tables_kernel<<<grid, 128, 0, stream>>>(variant, models, ne_kind, nu, n_nu, gamma, n_gamma,
                                                    mu, n_mu, phi, n_phi, ne_table, integ, p.n_pairs,
-                                                   gt, hull, ang, nt);
+                                                   gt, hull, raw, nt);
+        note_launch();
+        // sorted pair table (+ the polynomial rows of the np.trapz path)
+        const int n_seg = (p.n_pairs + kPairSeg - 1) / kPairSeg;
+        const int n_rb = v5 ? (n_nu + kTab2Threads / 32 - 1) / (kTab2Threads / 32) : 0;
+        dim3 grid2(n_seg + n_rb, n_models);
+        ec_tables2_kernel<<<grid2, kTab2Threads, 0, stream>>>(raw, p.n_pairs, n_seg, ang, models, nu,
+                                                              n_nu, gamma, n_gamma, gt, hull, rows);
         note_launch();
     }
     if (prefix) {
@@ -762,7 +1153,8 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         note_launch();
         return check_last("ec_sed (prefix)");
     }
-    size_t smem = (size_t)n_gamma * sizeof(double) * (integ == AGNPY_INTEG_TRAPZ ? 3 : 7);
+    size_t smem = v5 ? (size_t)ec_row_words(n_gamma) * sizeof(double) + 8
+                     : (size_t)n_gamma * sizeof(double) * (integ == AGNPY_INTEG_TRAPZ ? 3 : 7);
     if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for the EC kernel");
     // slice groups per (nu, model): a block walks all its slices once the grid fills the GPU
     // many times over (amortises the table copy), else one block per slice (latency)
@@ -780,6 +1172,40 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     }
     int iters = 1;
     while ((1 << iters) < n_gamma + 1) ++iters;
+    if (v5) {
+        const int row_words = ec_row_words(n_gamma);
+        // frequencies per block: as many as keep >= 8 waves of blocks in flight, at most 16
+        int L_nu = 16;
+        while (L_nu > 1 && (long long)p.S * ((n_nu + L_nu - 1) / L_nu) * n_models < 8LL * 5 * sms) L_nu >>= 1;
+        if (const char* e = getenv("AGNPY_B200_EC_LNU")) {  // development knob
+            int v = atoi(e);
+            if (v >= 1) L_nu = v;
+        }
+        const size_t row_bytes = (size_t)row_words * sizeof(double);
+        while (L_nu > 1 && L_nu * row_bytes > 52 * 1024) L_nu >>= 1;  // 4 blocks of rows per SM
+        dim3 grid(p.S, (n_nu + L_nu - 1) / L_nu, n_models);
+        const size_t smem6 = L_nu * (row_bytes + 8);
+        timing_begin(stream);
+#define EC_LAUNCH6(JJ)                                                                             \
+    do {                                                                                           \
+        if (smem6 > 48 * 1024)                                                                     \
+            cudaFuncSetAttribute(ec_main_poly_kernel<JJ>,                                          \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);         \
+        ec_main_poly_kernel<JJ><<<grid, p.T, smem6, stream>>>(models, nu, n_nu, gt, hull, n_gamma,  \
+                                                             rows, ang, p.n_pairs, p.S, L_nu, part); \
+    } while (0)
+        if (p.J == 8) EC_LAUNCH6(8);
+        else if (p.J == 4) EC_LAUNCH6(4);
+        else if (p.J == 2) EC_LAUNCH6(2);
+        else EC_LAUNCH6(1);
+#undef EC_LAUNCH6
+        timing_end(stream);
+        note_launch();
+        dim3 g2((n_nu + 127) / 128, n_models);
+        ec_finish_kernel<<<g2, 128, 0, stream>>>(variant, models, nu, n_nu, part, p.S * p.W(), sed);
+        note_launch();
+        return check_last("ec_sed");
+    }
     dim3 grid(Sg, n_nu, n_models);
     timing_begin(stream);
 #define EC_LAUNCH(I, JJ) launch_main<I, JJ>(grid, p.T, smem, stream, models, nu, n_nu, gt, hull, \
@@ -799,6 +1225,8 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         else if (p.J == 2) EC_LAUNCH32(2);
         else EC_LAUNCH32(1);
 #undef EC_LAUNCH32
+    } else if (v5) {
+        // handled above
     } else if (integ == AGNPY_INTEG_LOGLOG) EC_LAUNCH(AGNPY_INTEG_LOGLOG, 1);
     else if (p.J == 8) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 8);
     else if (p.J == 4) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 4);

@@ -13,7 +13,7 @@ inside the timed step.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
 ranks); `e2e` goes through the public host-buffer API (pinned H2D of the model table, D2H of
-the SEDs, wall clock); `roofline` is for the dominant kernel ec_main_kernel; `cpu_baseline` is
+the SEDs, wall clock); `roofline` is for the dominant kernel ec_main_poly_kernel; `cpu_baseline` is
 the oracle (reference arithmetic, 1 core) timed on this box.
 """
 import argparse
@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 MODELS_PER_GPU = 256
 N_NU, N_GAMMA, N_MU, N_PHI = 200, 200, 100, 50
 FLOPS_PER_POINT = 16          # nominal FP64 ops per compton_kernel point (np.trapz)
-EXEC_FLOPS_PER_POINT = 6      # executed: DMUL + DADD + DFMA + DFMA (FMA = 2)
+EXEC_FLOPS_PER_POINT = 4      # executed: 2 DFMA per visited point (polynomial form, FMA = 2)
 METRIC = "SED evals/sec (EC-BLR)"
 UNIT = "SED/s"
 WORKLOAD = ("configs[1]: ExternalCompton on SphericalShellBLR (Lyalpha), 200 nu x 200 gamma x "
@@ -387,7 +387,7 @@ def run_cuda(args):
                                    "agnpy_b200_ec_sed_host)"},
         "integrand_gpts_per_s": total * N_NU * N_GAMMA * N_MU * N_PHI / (ms_per_step * 1e-3) / 1e9,
         "roofline": {
-            "bound": "fp64", "kernel": "ec_main_kernel<trapz,J=4>", "achieved": achieved,
+            "bound": "fp64", "kernel": "ec_main_poly_kernel<J=8>", "achieved": achieved,
             "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
             "traffic": traffic,
             "peak_source": "live DFMA-chain microbenchmark agnpy_b200_fp64_peak on this GPU "
@@ -399,8 +399,9 @@ def run_cuda(args):
                          "visited_point_fraction": frac_pts},
             "note": "frac > 1 is expected: the nominal 16 flop/point charges two divisions and the "
                     "(gamma,nu)/(mu,phi)-only subexpressions per point; the kernel hoists them "
-                    "(4 FP64 instr/point) and skips points the reference masks to exactly 0. "
-                    "'executed' counts only instructions actually issued."},
+                    "(2 DFMA per point: wf*K = P + Q b^2 + R b with per-(gamma,nu) tables) and "
+                    "skips points the reference masks to exactly 0. 'executed' counts only the "
+                    "DFMAs actually issued on visited points."},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} SED(s) of the same workload (oracle = reference numpy "
                                    "arithmetic, nu-chunked by 25), 1 thread",

@@ -49,6 +49,37 @@ __global__ void __launch_bounds__(256) k(double* out, const double* tabs, int n,
                 }
                 G += 1e-9;  // keep the loop from collapsing
             }
+        } else if (MODE == 5) {  // v5 body: u = fma(Q,b,R); acc = fma(u,b,acc), {Q,R} one 16-byte smem read
+            const double2* qr = reinterpret_cast<const double2*>(sh);
+            for (int kk = 0; kk < n; ++kk) {
+                double2 v = qr[kk];
+#pragma unroll
+                for (int j = 0; j < J; ++j) acc[j] = fma(fma(v.x, bb[j], v.y), bb[j], acc[j]);
+            }
+        } else if (MODE == 6) {  // split body: acc = fma(Q,b^2,acc); acc = fma(R,b,acc)
+            const double2* qr = reinterpret_cast<const double2*>(sh);
+            double b2[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) b2[j] = bb[j] * bb[j];
+            for (int kk = 0; kk < n; ++kk) {
+                double2 v = qr[kk];
+#pragma unroll
+                for (int j = 0; j < J; ++j) acc[j] = fma(v.x, b2[j], acc[j]);
+#pragma unroll
+                for (int j = 0; j < J; ++j) acc[j] = fma(v.y, bb[j], acc[j]);
+            }
+        } else if (MODE == 7) {  // split body, two accumulator sets
+            const double2* qr = reinterpret_cast<const double2*>(sh);
+            double b2[J], acc2[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) { b2[j] = bb[j] * bb[j]; acc2[j] = 0.0; }
+            for (int kk = 0; kk < n; ++kk) {
+                double2 v = qr[kk];
+#pragma unroll
+                for (int j = 0; j < J; ++j) { acc[j] = fma(v.x, b2[j], acc[j]); acc2[j] = fma(v.y, bb[j], acc2[j]); }
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] += acc2[j];
         } else if (MODE == 4) {  // factored form: 2 DFMA per point, tables from shared memory
             for (int kk = 0; kk < n; ++kk) {
                 double H = sh[kk], G = sh[2 * n + kk];
@@ -99,5 +130,13 @@ int main() {
     run<3, 8>("EC body, register 'tables'", 4, 256, 4);
     run<4, 4>("factored body (2 DFMA), smem tables", 8, 256, 2);
     run<4, 8>("factored body (2 DFMA), smem tables", 4, 256, 2);
+    run<5, 8>("v5 body (2 DFMA, 3 reg operands), smem", 4, 128, 2);
+    run<5, 8>("v5 body (2 DFMA, 3 reg operands), smem", 7, 128, 2);
+    run<5, 4>("v5 body (2 DFMA, 3 reg operands), smem", 8, 128, 2);
+    run<6, 8>("split body (Q b^2 + R b), smem", 4, 128, 2);
+    run<6, 8>("split body (Q b^2 + R b), smem", 7, 128, 2);
+    run<6, 4>("split body (Q b^2 + R b), smem", 8, 128, 2);
+    run<7, 8>("split body, 2 accumulator sets, smem", 4, 128, 2);
+    run<7, 4>("split body, 2 accumulator sets, smem", 8, 128, 2);
     return 0;
 }

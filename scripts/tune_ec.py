@@ -25,16 +25,19 @@ def run(n_models, reps=8):
     return e0.elapsed_time(e1) / reps, kms / max(kn, 1), d_out.cpu().numpy()
 
 ref = None
-for plan_s in (None, "256,4", "128,8", "128,4", "64,8"):
-    for sg in (None, "1"):
+variants = [(None, p, sg) for p in (None, "128,4", "64,8") for sg in (None, "2", "4")]
+for v4, plan_s, sg in variants:
+    if True:
+        if v4: os.environ["AGNPY_B200_EC_V4"] = v4
+        else: os.environ.pop("AGNPY_B200_EC_V4", None)
         if plan_s: os.environ["AGNPY_B200_EC_PLAN"] = plan_s
         else: os.environ.pop("AGNPY_B200_EC_PLAN", None)
-        if sg: os.environ["AGNPY_B200_EC_SG"] = sg
-        else: os.environ.pop("AGNPY_B200_EC_SG", None)
+        if sg: os.environ["AGNPY_B200_EC_LNU"] = sg
+        else: os.environ.pop("AGNPY_B200_EC_LNU", None)
         res = []
-        for n in (1, 64):
+        for n in (1, 64, 256):
             ms, kms, out = run(n)
             if ref is None and n == 64: ref = out
-            if n == 64: dev = float(np.nanmax(np.abs(out / np.where(ref != 0, ref, 1) - 1) * (ref != 0)))
+            if n >= 64: dev = float(np.nanmax(np.abs(out[:64] / np.where(ref != 0, ref, 1) - 1) * (ref != 0)))
             res.append(f"n={n}: {ms*1e3:8.1f} us (main {kms*1e3:8.1f} us)")
-        print(f"plan={plan_s} sg={sg}: " + " | ".join(res) + f" | dev vs first {dev:.1e}", flush=True)
+        print(f"v4={v4} plan={plan_s} sg={sg}: " + " | ".join(res) + f" | dev vs first {dev:.1e}", flush=True)
