@@ -119,13 +119,15 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         return fail(AGNPY_ERR_ARG, "ssc_sed: AGNPY_NE_TABLE needs n_e (and SSA) tables");
     integ = plain_integ(integ);
     cudaStream_t stream = (cudaStream_t)stream_;
-    size_t per = (3 * (size_t)n_gamma + 2 * (size_t)n_seed) * sizeof(double);
+    size_t per = (3 * (size_t)n_gamma + 2 * (size_t)n_seed + ssc_scratch_doubles(n_gamma, n_seed)) *
+                 sizeof(double);
     int chunk = chunk_models(per, n_models);
     double* ws = (double*)workspace(per * chunk, stream);
     if (!ws) return fail(AGNPY_ERR_NOMEM, "ssc_sed: workspace");
     for (int m0 = 0; m0 < n_models; m0 += chunk) {
         int nm = std::min(chunk, n_models - m0);
-        double* tab = ws;
+        double* scratch = ws;  // first: 32-byte aligned rows of the np.trapz path
+        double* tab = scratch + (size_t)nm * ssc_scratch_doubles(n_gamma, n_seed);
         double* U = tab + (size_t)nm * 3 * n_gamma;
         double* es = U + (size_t)nm * n_seed;
         launch_prep_gamma(models + m0, nm, ne_kind, gamma, n_gamma, row_at(ne_table, m0, n_gamma),
@@ -134,10 +136,8 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         if (int rc = launch_synch(models + m0, nm, nu_seed, n_seed, tab, n_gamma, ssa, integ, 1, U,
                                   nullptr, es, stream))
             return rc;
-        timing_begin(stream);
         int rc_ssc = launch_ssc(models + m0, nm, nu, n_nu, tab, n_gamma, U, es, n_seed, integ,
-                                sed + (size_t)m0 * n_nu, stream);
-        timing_end(stream);
+                                sed + (size_t)m0 * n_nu, scratch, stream);
         if (rc_ssc) return rc_ssc;
     }
     return check_last("ssc_sed");

@@ -16,9 +16,11 @@ int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, in
 int launch_ssc_loss_rate(int n_models, const double* gamma_eval, int n_eval, const double* U_seed,
                          const double* eps_seed, int n_seed, double* out, cudaStream_t stream);
 
+// `scratch`: ssc_scratch_doubles(n_gamma, n_seed) doubles per model, 32-byte aligned
+size_t ssc_scratch_doubles(int n_gamma, int n_seed);
 int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,
-               int n_seed, int integ, double* out, cudaStream_t stream);
+               int n_seed, int integ, double* out, double* scratch, cudaStream_t stream);
 
 // bytes of scratch the EC / tau pipelines need for `n_models` models
 size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi);

@@ -336,26 +336,182 @@ __global__ void __launch_bounds__(256) ssc_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2, np.trapz path (v2): one warp per (nu, model).  The valid region of the (seed eps_j, gamma_k)
+// plane is a band -- q <= 1 bounds j from below, q >= q_min from above, for every k -- so the
+// warp takes the gamma axis 32 points at a time (lane l owns one gamma_k: h, ln h, c1 and an
+// accumulator in registers) and walks the seed axis over the union of the lanes' bands; the
+// per-seed constants arrive as one warp-uniform 32-byte load.  A visited
+// point costs 7 FP64 instructions (kernels.py:17-33 rewritten as in the kernel above):
+//     s = 2h/eps_j (= 2q);  ln q = ln h - ln eps_j;  F = s ln q + (1 - s/2)(c1 + s);
+//     acc_k += (w_j U_j) F            and at the end  total += (w_k N_e/gamma_k^2) acc_k.
+// No masked point is evaluated and no mask is tested in the loop: per (k, nu) the seed range
+// that is surely inside (q_min(1+1e-12) <= q <= 1-1e-12) is located by binary search on the
+// monotone q(j); the at most few seeds inside the 1e-12 bands around the two boundaries are
+// decided and evaluated with the reference's own operation order (Fc_exact).
+// ssc_prep_kernel tabulates what does not depend on nu, once per model:
+//   gk[m][k] = {gamma_k, 1/gamma_k, ln(4 gamma_k^2), w_k N_e/gamma_k^2}     (32 bytes)
+//   sj[m][j] = {1/eps_j, -ln eps_j, w_j U_j, eps_j}                          (32 bytes)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ssc_prep_kernel(
+    const double* __restrict__ tab, int n_gamma, const double* __restrict__ U_seed,
+    const double* __restrict__ eps_seed, int n_seed, double4* __restrict__ gk,
+    double4* __restrict__ sj) {
+    const int m = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* gs = tab + (size_t)m * 3 * n_gamma;
+    const double* Ne = gs + n_gamma;
+    if (t < n_gamma) {
+        const double g = gs[t];
+        const double f = Ne[t] / (g * g) * trapz_weight(gs, t, n_gamma);
+        gk[(size_t)m * n_gamma + t] = make_double4(g, 1.0 / g, log(4.0 * (g * g)), f);
+    }
+    if (t < n_seed) {
+        const double* es = eps_seed + (size_t)m * n_seed;
+        const double eps = es[t];
+        const double w = trapz_weight(es, t, n_seed);
+        sj[(size_t)m * n_seed + t] =
+            make_double4(1.0 / eps, -log(eps), w * U_seed[(size_t)m * n_seed + t], eps);
+    }
+}
+
+// first j in [0, n) with pred(j) true, for a predicate that is false...true along j; `j` is a
+// guess (exact for a log-uniform seed grid up to rounding): a couple of probes around it, a
+// binary search of the rest if the guess is far off (arbitrary grids)
+template <class Pred>
+__device__ __forceinline__ int first_true_near(int j, int n, Pred pred) {
+    j = max(0, min(j, n));
+    int steps = 0;
+    while (j > 0 && pred(j - 1)) { --j; if (++steps > 3) break; }
+    if (steps <= 3) {
+        steps = 0;
+        while (j < n && !pred(j)) { ++j; if (++steps > 3) break; }
+        if (steps <= 3) return j;
+    }
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (pred(mid)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// block = NW warps (blockDim.x / 32): warp w takes the gamma slots w, w + NW, ...
+__global__ void __launch_bounds__(256) ssc_trapz_kernel(
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu, int n_gamma,
+    const double4* __restrict__ gk_all, const double4* __restrict__ sj_all, int n_seed,
+    double* __restrict__ out) {
+    __shared__ double s_part[8];
+    const int m = blockIdx.y, i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    const agnpy_model_t& M = models[m];
+    const double4* gk = gk_all + (size_t)m * n_gamma;
+    const double4* sj = sj_all + (size_t)m * n_seed;
+    const double eps_s = nu_to_eps(nu[i], M.z, M.delta_D);
+    const double l_eps_s = log(eps_s);
+    // ln eps_j ~ l0 + j dl on a log-uniform seed grid: starting guess of the range searches
+    const double l0 = -sj[0].y;
+    const double inv_dl = (double)(n_seed - 1) / (-sj[n_seed - 1].y - l0);
+    double total = 0.0;
+    for (int k0 = 32 * warp; k0 < n_gamma; k0 += 32 * n_warps) {
+        const int k = k0 + lane;
+        double h2 = 0.0, lh = 0.0, c1 = 0.0, acc = 0.0, fw = 0.0;
+        int ja = n_seed, jb = -1;  // seeds surely inside the mask for this lane's gamma
+        if (k < n_gamma) {
+            const double4 G = gk[k];  // {gamma, 1/gamma, ln 4 gamma^2, w N_e/gamma^2}
+            const double u = eps_s * G.y;
+            fw = G.w;
+            if (G.w != 0.0 && u < 1.0) {  // gamma <= eps_s: q < 0 or undefined, never inside
+                const double v = u / (1.0 - u);
+                const double h = v * (0.25 * G.y);
+                const double qmin = 0.25 * (G.y * G.y);
+                const double q_in_lo = qmin * (1.0 + kGuard), q_out_lo = qmin * (1.0 - kGuard);
+                h2 = h + h;
+                lh = l_eps_s - G.z - log1p(-u);
+                c1 = 1.0 + 0.5 * (v * v) / (1.0 + v);
+                // candidates: q <= 1+guard and q >= q_min (1-guard); q(j) = h/eps_j falls with j
+                int a = first_true_near((int)ceil((lh - l0) * inv_dl), n_seed,
+                                        [&](int j) { return h * sj[j].x <= 1.0 + kGuard; });
+                int b = first_true_near((int)ceil((lh + G.z - l0) * inv_dl), n_seed,
+                                        [&](int j) { return h * sj[j].x < q_out_lo; }) - 1;
+                // shrink to the surely-inside range; what is cut off is decided exactly
+                while (a <= b && !(h * sj[a].x <= 1.0 - kGuard)) {
+                    bool in;
+                    double F = Fc_exact(G.x, sj[a].w, eps_s, in);
+                    if (in) acc = fma(sj[a].z, F, acc);
+                    ++a;
+                }
+                while (b >= a && !(h * sj[b].x >= q_in_lo)) {
+                    bool in;
+                    double F = Fc_exact(G.x, sj[b].w, eps_s, in);
+                    if (in) acc = fma(sj[b].z, F, acc);
+                    --b;
+                }
+                ja = a;
+                jb = b;
+            }
+        }
+        const int JA = __reduce_min_sync(0xffffffffu, ja);
+        const int JB = __reduce_max_sync(0xffffffffu, jb);
+#pragma unroll 4
+        for (int j = JA; j <= JB; ++j) {
+            const double4 c = sj[j];  // warp-uniform: {1/eps_j, -ln eps_j, w_j U_j, eps_j}
+            if (j >= ja && j <= jb) {
+                const double sq = h2 * c.x;            // 2q
+                const double lq = lh + c.y;            // ln q
+                const double t = fma(-0.5, sq, 1.0);   // 1 - q
+                const double F = fma(sq, lq, t * (c1 + sq));
+                acc = fma(c.z, F, acc);
+            }
+        }
+        total = fma(fw, acc, total);
+    }
+    total = warp_sum(total);
+    if (lane == 0) s_part[warp] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < n_warps; ++w) sum += s_part[w];
+        // synchrotron_self_compton.py:156-158
+        double emissivity = 3.0 / 4.0 * kC * kSigmaT * (eps_s * eps_s) * sum;
+        double prefactor = (M.delta_D * M.delta_D * M.delta_D * M.delta_D) /
+                           (4.0 * kPi * (M.d_L * M.d_L));
+        out[(size_t)m * n_nu + i] = prefactor * emissivity;
+    }
+}
+
+size_t ssc_scratch_doubles(int n_gamma, int n_seed) { return 4 * ((size_t)n_gamma + n_seed); }
+
 int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
                const double* tab, int n_gamma, const double* U_seed, const double* eps_seed,
-               int n_seed, int integ, double* out, cudaStream_t stream) {
-    dim3 grid(n_nu, n_models);
-    size_t smem = (integ == AGNPY_INTEG_LOGLOG ? 9 * (size_t)n_gamma + n_seed : 13 * (size_t)n_gamma + 2) *
-                  sizeof(double);
-    if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for ssc kernel");
+               int n_seed, int integ, double* out, double* scratch, cudaStream_t stream) {
     if (integ == AGNPY_INTEG_TRAPZ) {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(ssc_kernel<AGNPY_INTEG_TRAPZ>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ssc_kernel<AGNPY_INTEG_TRAPZ><<<grid, 256, smem, stream>>>(
-            models, nu, n_nu, tab, n_gamma, U_seed, eps_seed, n_seed, out);
-    } else {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(ssc_kernel<AGNPY_INTEG_LOGLOG>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ssc_kernel<AGNPY_INTEG_LOGLOG><<<grid, 256, smem, stream>>>(
-            models, nu, n_nu, tab, n_gamma, U_seed, eps_seed, n_seed, out);
+        double4* gk = reinterpret_cast<double4*>(scratch);
+        double4* sj = gk + (size_t)n_models * n_gamma;
+        int nmax = n_gamma > n_seed ? n_gamma : n_seed;
+        dim3 g1((nmax + 127) / 128, n_models);
+        ssc_prep_kernel<<<g1, 128, 0, stream>>>(tab, n_gamma, U_seed, eps_seed, n_seed, gk, sj);
+        note_launch();
+        dim3 grid(n_nu, n_models);
+        timing_begin(stream);
+        // one warp per (nu, model) once the grid fills the GPU; small grids spread the gamma slots
+        // of a row over up to 8 warps (latency of a single call)
+        int slots = (n_gamma + 31) / 32, nw = 1;
+        while (nw < 8 && nw < slots && (long long)n_nu * n_models * nw < 4096) nw <<= 1;
+        ssc_trapz_kernel<<<grid, 32 * nw, 0, stream>>>(models, nu, n_nu, n_gamma, gk, sj, n_seed, out);
+        timing_end(stream);
+        note_launch();
+        return AGNPY_OK;
     }
+    dim3 grid(n_nu, n_models);
+    size_t smem = (9 * (size_t)n_gamma + n_seed) * sizeof(double);
+    if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for ssc kernel");
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(ssc_kernel<AGNPY_INTEG_LOGLOG>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    timing_begin(stream);
+    ssc_kernel<AGNPY_INTEG_LOGLOG><<<grid, 256, smem, stream>>>(
+        models, nu, n_nu, tab, n_gamma, U_seed, eps_seed, n_seed, out);
+    timing_end(stream);
     note_launch();
     return AGNPY_OK;
 }
