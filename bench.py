@@ -349,7 +349,7 @@ def run_cuda(args):
             "value": MODELS_PER_GPU / (ssc_ms * 1e-3), "unit": UNIT, "ms_per_step": ssc_ms,
             "workload": "configs[0]: SSC of the tutorial blob, 100 nu x 200 seed nu x 200 gamma, "
                         "np.trapz, 256 models per step (seed synchrotron spectrum included)",
-            "kernel": "ssc_kernel<trapz>", "kernel_ms": ssc_kms,
+            "kernel": "ssc_trapz_kernel", "kernel_ms": ssc_kms,
             "integrand_gpts_per_s": ssc_pts / (ssc_ms * 1e-3) / 1e9,
             "roofline_frac_algorithmic": ssc_pts * 24 / (ssc_kms * 1e-3) / peak,
             "algorithmic_flops_per_point": 24, "parity_max_rel_dev": ssc_dev},
