@@ -73,6 +73,42 @@ void launch_prep_gamma(const agnpy_model_t* models, int n_models, int ne_kind, c
 // u_synch of blob.py:395-404, plus eps written to eps_out;  out_mode 2 (opacity on the
 // synchrotron field): photon density n_synch(eps) of targets_absorption.py:671-684, plus eps.
 // ---------------------------------------------------------------------------------------------
+// flux / seed-field / photon-density epilogue of one (nu, model): synchrotron.py:122-129,192-211
+__device__ __forceinline__ void synch_store(const agnpy_model_t& M, double eps, double acc,
+                                            double acc_ssa, int ssa, int out_mode, int n_nu, int m,
+                                            int i, double* __restrict__ out,
+                                            double* __restrict__ tau_out,
+                                            double* __restrict__ eps_out) {
+    double prefactor = (M.delta_D * M.delta_D * M.delta_D * M.delta_D) /
+                       (4.0 * kPi * (M.d_L * M.d_L));  // :192
+    double sed = prefactor * eps * acc;
+    if (ssa) {
+        // :122-129  k_eps = -1/(8 pi m_e eps^2) (lambda_c/c)^3 * integral ; tau = 2 k_eps R_b
+        double lc = kLambdaC / kC;
+        double pk = -1.0 / (8.0 * kPi * kMe * (eps * eps)) * (lc * lc * lc);
+        double tau = 2.0 * (pk * acc_ssa) * M.R_b;
+        sed = sed * ssa_attenuation(tau);
+        if (tau_out) tau_out[(size_t)m * n_nu + i] = tau;
+    }
+    if (out_mode == 0) {
+        out[(size_t)m * n_nu + i] = sed;
+    } else if (out_mode == 2) {
+        // photon density of the synchrotron field per unit eps, targets_absorption.py:671-684
+        double n_synch = (3.0 * (M.d_L * M.d_L) * sed) /
+                         (kC * (M.R_b * M.R_b) * (M.delta_D * M.delta_D * M.delta_D * M.delta_D) *
+                          (eps * eps) * kMe * (kC * kC));
+        out[(size_t)m * n_nu + i] = n_synch * (3.0 / 4.0);
+        eps_out[(size_t)m * n_nu + i] = eps;
+    } else {
+        // blob.py:395-404 then the 1/eps^2 of synchrotron_self_compton.py:152
+        double u = (3.0 * (M.d_L * M.d_L) * sed) /
+                   (kC * (M.R_b * M.R_b) * (M.delta_D * M.delta_D * M.delta_D * M.delta_D) * eps);
+        u = u * (3.0 / 4.0);
+        out[(size_t)m * n_nu + i] = u / (eps * eps);
+        eps_out[(size_t)m * n_nu + i] = eps;
+    }
+}
+
 template <int INTEG>
 __global__ void __launch_bounds__(128) synch_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
@@ -130,35 +166,74 @@ __global__ void __launch_bounds__(128) synch_kernel(
     }
     acc = block_sum(acc, red);
     if (ssa) acc_ssa = block_sum(acc_ssa, red);
-    if (threadIdx.x == 0) {
-        double prefactor = (M.delta_D * M.delta_D * M.delta_D * M.delta_D) /
-                           (4.0 * kPi * (M.d_L * M.d_L));  // :192
-        double sed = prefactor * eps * acc;
-        if (ssa) {
-            // :122-129  k_eps = -1/(8 pi m_e eps^2) (lambda_c/c)^3 * integral ; tau = 2 k_eps R_b
-            double lc = kLambdaC / kC;
-            double pk = -1.0 / (8.0 * kPi * kMe * (eps * eps)) * (lc * lc * lc);
-            double tau = 2.0 * (pk * acc_ssa) * M.R_b;
-            sed = sed * ssa_attenuation(tau);
-            if (tau_out) tau_out[(size_t)m * n_nu + i] = tau;
+    if (threadIdx.x == 0) synch_store(M, eps, acc, acc_ssa, ssa, out_mode, n_nu, m, i, out, tau_out, eps_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, np.trapz path on large grids: one warp per (kSynTN frequencies, model).  Lane l owns gamma_k, k = l, l+32,
+// ...; per gamma it forms 1/gamma^2 and gamma^(-2/3) once and reuses them for the kSynTN
+// frequencies of the warp, so R(x) of synchrotron.py:16-24 costs no cube root and one division
+// per point:  x = X_nu / gamma^2 (one rounding away from the reference's xnum/(xden gamma^2)),
+// x^(1/3) = X_nu^(1/3) gamma^(-2/3),  R = 1.808 x^(1/3) (1+2.21x^(2/3)+0.347x^(4/3)) e^-x
+//                                         / (sqrt(1+3.4x^(2/3)) (1+1.353x^(2/3)+0.217x^(4/3))).
+// Points with x > 746 are skipped: e^-x is exactly 0 there in the reference too.  The gamma sum
+// is a per-lane FMA chain joined by one shuffle reduction per frequency (no shared memory).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSynTN = 4;
+__global__ void __launch_bounds__(32) synch_trapz_kernel(
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
+    const double* __restrict__ tab, int n_gamma, int ssa, int out_mode,
+    double* __restrict__ out, double* __restrict__ tau_out, double* __restrict__ eps_out,
+    int nu_stride, int proton) {
+    const int m = blockIdx.y, i0 = blockIdx.x * kSynTN, lane = threadIdx.x;
+    const agnpy_model_t& M = models[m];
+    const double* gs = tab + (size_t)m * 3 * n_gamma;
+    const double* Ne = gs + n_gamma;
+    const double* Sa = gs + 2 * n_gamma;
+    const double mass = proton ? kMp : kMe;
+    const double B = M.B;
+    const double xden = 3.0 * kE * B * kH;
+    const double prefP = sqrt(3.0) * (kE * kE * kE) * B / kH;  // synchrotron.py:59
+    double eps[kSynTN], X[kSynTN], X13[kSynTN], acc[kSynTN], acc_ssa[kSynTN];
+#pragma unroll
+    for (int q = 0; q < kSynTN; ++q) {
+        const int i = min(i0 + q, n_nu - 1);
+        const double nu_i = nu[(size_t)m * nu_stride + i];
+        eps[q] = proton ? (1.0 + M.z) * (kH * nu_i / kMpc2) / M.delta_D : nu_to_eps(nu_i, M.z, M.delta_D);
+        // synchrotron.py:35-47: x = 4 pi eps m^2 c^3 / (3 e B h gamma^2)
+        X[q] = (4.0 * kPi * eps[q] * (mass * mass) * (kC * kC * kC)) / xden;
+        X13[q] = cbrt(X[q]);
+        acc[q] = 0.0;
+        acc_ssa[q] = 0.0;
+    }
+    for (int k = lane; k < n_gamma; k += 32) {
+        const double g = gs[k];
+        const double ne = Ne[k], sa = ssa ? Sa[k] : 0.0;
+        if (ne == 0.0 && sa == 0.0) continue;
+        const double w = trapz_weight(gs, k, n_gamma);
+        const double ig2 = 1.0 / (g * g);
+        const double gm23 = cbrt(ig2);
+        const double wne = w * ne, wsa = w * sa;
+#pragma unroll
+        for (int q = 0; q < kSynTN; ++q) {
+            const double x = X[q] * ig2;
+            if (x > 746.0) continue;
+            const double x13 = X13[q] * gm23;
+            const double x23 = x13 * x13;
+            const double x43 = x23 * x23;
+            const double num = 1.808 * x13 * fma(0.347, x43, fma(2.21, x23, 1.0));
+            const double den = sqrt(fma(3.4, x23, 1.0)) * fma(0.217, x43, fma(1.353, x23, 1.0));
+            const double P = prefP * (num / den * exp(-x));
+            acc[q] = fma(wne, P, acc[q]);
+            acc_ssa[q] = fma(wsa, P, acc_ssa[q]);
         }
-        if (out_mode == 0) {
-            out[(size_t)m * n_nu + i] = sed;
-        } else if (out_mode == 2) {
-            // photon density of the synchrotron field per unit eps, targets_absorption.py:671-684
-            double n_synch = (3.0 * (M.d_L * M.d_L) * sed) /
-                             (kC * (M.R_b * M.R_b) * (M.delta_D * M.delta_D * M.delta_D * M.delta_D) *
-                              (eps * eps) * kMe * (kC * kC));
-            out[(size_t)m * n_nu + i] = n_synch * (3.0 / 4.0);
-            eps_out[(size_t)m * n_nu + i] = eps;
-        } else {
-            // blob.py:395-404 then the 1/eps^2 of synchrotron_self_compton.py:152
-            double u = (3.0 * (M.d_L * M.d_L) * sed) /
-                       (kC * (M.R_b * M.R_b) * (M.delta_D * M.delta_D * M.delta_D * M.delta_D) * eps);
-            u = u * (3.0 / 4.0);
-            out[(size_t)m * n_nu + i] = u / (eps * eps);
-            eps_out[(size_t)m * n_nu + i] = eps;
-        }
+    }
+#pragma unroll
+    for (int q = 0; q < kSynTN; ++q) {
+        const double a = warp_sum(acc[q]);
+        const double as = ssa ? warp_sum(acc_ssa[q]) : 0.0;
+        if (lane == 0 && i0 + q < n_nu)
+            synch_store(M, eps[q], a, as, ssa, out_mode, n_nu, m, i0 + q, out, tau_out, eps_out);
     }
 }
 
@@ -167,8 +242,16 @@ int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, in
                  double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride, int proton) {
     dim3 grid(n_nu, n_models);
     if (integ == AGNPY_INTEG_TRAPZ) {
-        synch_kernel<AGNPY_INTEG_TRAPZ><<<grid, 128, 0, stream>>>(
-            models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride, proton);
+        // 4 frequencies per warp amortise the per-gamma cube root once the grid fills the GPU; a
+        // small grid (single call) keeps one block per frequency: shortest dependent chain
+        if ((long long)n_nu * n_models >= 8192) {
+            dim3 g4((n_nu + 3) / 4, n_models);
+            synch_trapz_kernel<<<g4, 32, 0, stream>>>(models, nu, n_nu, tab, n_gamma, ssa, out_mode,
+                                                         out, tau_out, eps_out, nu_stride, proton);
+        } else {
+            synch_kernel<AGNPY_INTEG_TRAPZ><<<grid, 128, 0, stream>>>(
+                models, nu, n_nu, tab, n_gamma, ssa, out_mode, out, tau_out, eps_out, nu_stride, proton);
+        }
     } else {
         size_t smem = 2 * (size_t)n_gamma * sizeof(double);
         if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for trapz_loglog");
