@@ -110,3 +110,32 @@ def ssc_loss_rate_host(models, ne_kind, gamma_eval, nu_seed, gamma, ne_table=Non
         n, hptr(models), ne_kind, hptr(gamma_eval), gamma_eval.size, hptr(nu_seed), nu_seed.size,
         hptr(gamma), gamma.size, hptr(ne_table), hptr(out)), "agnpy_b200_ssc_loss_rate_host")
     return out
+
+
+def target_u_host(variant, models, r, Gamma=None, n_mu=50):
+    r = f64(np.ravel(r))
+    n = len(models)
+    Gamma = None if Gamma is None else f64(np.broadcast_to(Gamma, (n,)).copy())
+    out = np.empty((n, r.size))
+    check(lib().agnpy_b200_target_u_host(variant, n, hptr(models), hptr(Gamma), hptr(r), r.size,
+                                         int(n_mu), hptr(out)), "agnpy_b200_target_u_host")
+    return out
+
+
+def ebl_absorption_host(z, nu, energy_ref, z_ref, values, sed=None):
+    """absorption [n_models][n_nu]; with `sed` ([n_models][n_nu], C-contiguous float64) the
+    table is applied in place and `sed` is returned"""
+    z, nu = f64(np.atleast_1d(z)), f64(np.ravel(nu))
+    energy_ref, z_ref, values = f64(energy_ref), f64(z_ref), f64(values)
+    if values.shape != (energy_ref.size, z_ref.size):
+        raise ValueError("EBL table must be values[n_energy][n_z]")
+    if sed is None:
+        out, mult = np.empty((z.size, nu.size)), 0
+    else:
+        if sed.shape != (z.size, nu.size) or sed.dtype != np.float64 or not sed.flags.c_contiguous:
+            raise ValueError("sed must be a C-contiguous float64 array [n_models][n_nu]")
+        out, mult = sed, 1
+    check(lib().agnpy_b200_ebl_absorption_host(z.size, hptr(z), hptr(nu), nu.size, hptr(energy_ref),
+                                               energy_ref.size, hptr(z_ref), z_ref.size, hptr(values),
+                                               mult, hptr(out)), "agnpy_b200_ebl_absorption_host")
+    return out

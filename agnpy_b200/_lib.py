@@ -31,6 +31,8 @@ EXPORTS = [
     "agnpy_b200_proton_synch_sed", "agnpy_b200_proton_synch_sed_host",
     "agnpy_b200_ssc_loss_rate", "agnpy_b200_ssc_loss_rate_host",
     "agnpy_b200_bb_sed", "agnpy_b200_bb_sed_host",
+    "agnpy_b200_target_u", "agnpy_b200_target_u_host",
+    "agnpy_b200_ebl_absorption", "agnpy_b200_ebl_absorption_host",
 ]
 
 
@@ -94,6 +96,12 @@ def lib():
     bb = [ip, ip, dp, dp, ip, dp, ip, ip, dp]
     L.agnpy_b200_bb_sed.argtypes = bb + [vp]
     L.agnpy_b200_bb_sed_host.argtypes = bb
+    tu = [ip, ip, dp, dp, dp, ip, ip, dp]
+    L.agnpy_b200_target_u.argtypes = tu + [vp]
+    L.agnpy_b200_target_u_host.argtypes = tu
+    ebl = [ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
+    L.agnpy_b200_ebl_absorption.argtypes = ebl + [vp]
+    L.agnpy_b200_ebl_absorption_host.argtypes = ebl
     L.agnpy_b200_kernel_timing.argtypes = [C.c_int]
     L.agnpy_b200_kernel_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     for name in EXPORTS[3:]:

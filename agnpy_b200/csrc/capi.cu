@@ -312,6 +312,33 @@ int agnpy_b200_bb_sed(int variant, int n_models, const agnpy_model_t* models, co
                   (cudaStream_t)stream_);
 }
 
+// ------------------------------------------------------------------------------------------
+int agnpy_b200_target_u(int variant, int n_models, const agnpy_model_t* models, const double* Gamma,
+                        const double* r, int n_r, int n_mu, double* u, void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (variant != AGNPY_EC_PS_BEHIND_JET && variant != AGNPY_EC_SS_DISK && variant != AGNPY_EC_BLR &&
+        variant != AGNPY_EC_DT)
+        return fail(AGNPY_ERR_ARG, "target_u: bad variant");
+    if (n_models < 1 || n_r < 1 || !models || !r || !u)
+        return fail(AGNPY_ERR_ARG, "target_u: bad sizes or null pointer");
+    if ((variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR) && n_mu < 2)
+        return fail(AGNPY_ERR_ARG, "target_u: n_mu < 2");
+    if (n_models > 65535) return fail(AGNPY_ERR_ARG, "target_u: n_models > 65535");
+    return run_target_u(variant, models, n_models, Gamma, r, n_r, n_mu, u, (cudaStream_t)stream_);
+}
+
+int agnpy_b200_ebl_absorption(int n_models, const double* z, const double* nu, int n_nu,
+                              const double* energy_ref, int n_e, const double* z_ref, int n_z,
+                              const double* values, int multiply, double* out, void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || n_e < 2 || n_z < 2 || !z || !nu || !energy_ref || !z_ref ||
+        !values || !out)
+        return fail(AGNPY_ERR_ARG, "ebl_absorption: bad sizes or null pointer");
+    if (n_models > 65535) return fail(AGNPY_ERR_ARG, "ebl_absorption: n_models > 65535");
+    return run_ebl(n_models, z, nu, n_nu, energy_ref, n_e, z_ref, n_z, values, multiply, out,
+                   (cudaStream_t)stream_);
+}
+
 }  // extern "C"
 
 // ==========================================================================================
@@ -601,6 +628,49 @@ int agnpy_b200_ssc_loss_rate_host(int n_models, const agnpy_model_t* models, int
     if (int rc = agnpy_b200_ssc_loss_rate(n_models, io.dev<agnpy_model_t>(i_m), ne_kind, io.dev<double>(i_ge),
                                           n_eval, io.dev<double>(i_sd), n_seed, io.dev<double>(i_g), n_gamma,
                                           io.dev<double>(i_ne), io.dev<double>(o), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_target_u_host(int variant, int n_models, const agnpy_model_t* models,
+                             const double* Gamma, const double* r, int n_r, int n_mu, double* u) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_r < 1 || !models || !r || !u)
+        return fail(AGNPY_ERR_ARG, "target_u_host: bad sizes or null pointer");
+    HostIO io;
+    int i_m = io.in(models, sizeof(agnpy_model_t) * n_models), i_G = io.in(Gamma, 8 * (size_t)n_models);
+    int i_r = io.in(r, 8 * (size_t)n_r);
+    int o = io.out(u, 8 * (size_t)n_models * n_r);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_target_u(variant, n_models, io.dev<agnpy_model_t>(i_m), io.dev<double>(i_G),
+                                     io.dev<double>(i_r), n_r, n_mu, io.dev<double>(o), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_ebl_absorption_host(int n_models, const double* z, const double* nu, int n_nu,
+                                   const double* energy_ref, int n_e, const double* z_ref, int n_z,
+                                   const double* values, int multiply, double* out) {
+    if (int rc = need_device()) return rc;
+    if (n_models < 1 || n_nu < 1 || n_e < 2 || n_z < 2 || !z || !nu || !energy_ref || !z_ref ||
+        !values || !out)
+        return fail(AGNPY_ERR_ARG, "ebl_absorption_host: bad sizes or null pointer");
+    const size_t out_bytes = 8 * (size_t)n_models * n_nu;
+    HostIO io;
+    int i_z = io.in(z, 8 * (size_t)n_models), i_nu = io.in(nu, 8 * (size_t)n_nu);
+    int i_e = io.in(energy_ref, 8 * (size_t)n_e), i_zr = io.in(z_ref, 8 * (size_t)n_z);
+    int i_v = io.in(values, 8 * (size_t)n_e * n_z);
+    int i_sed = io.in(multiply ? out : nullptr, out_bytes);  // in-place flavour: the SEDs go up too
+    int o = io.out(out, out_bytes);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (multiply && cudaMemcpyAsync(io.dev<double>(o), io.dev<double>(i_sed), out_bytes,
+                                    cudaMemcpyDeviceToDevice, io.st) != cudaSuccess)
+        return check_last("ebl_absorption_host: D2D copy");
+    if (int rc = agnpy_b200_ebl_absorption(n_models, io.dev<double>(i_z), io.dev<double>(i_nu), n_nu,
+                                           io.dev<double>(i_e), n_e, io.dev<double>(i_zr), n_z,
+                                           io.dev<double>(i_v), multiply, io.dev<double>(o), io.st))
         return rc;
     return io.download();
 }

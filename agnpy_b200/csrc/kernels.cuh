@@ -43,4 +43,10 @@ int run_tau_synch(const agnpy_model_t* models, int n_models, int ne_kind, const 
 int run_bb(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
            const double* nu_norm, int n_norm, int n_R, double* sed, cudaStream_t stream);
 
+int run_target_u(int variant, const agnpy_model_t* models, int n_models, const double* Gamma,
+                 const double* r, int n_r, int n_mu, double* u, cudaStream_t stream);
+int run_ebl(int n_models, const double* z, const double* nu, int n_nu, const double* e_ref, int n_e,
+            const double* z_ref, int n_z, const double* values, int multiply, double* out,
+            cudaStream_t stream);
+
 }  // namespace agb

@@ -98,7 +98,7 @@ class FitSedBatch:
     all-gather joins the summed SEDs."""
 
     def __init__(self, nu, ne_kind="BrokenPowerLaw", scenario="ec_blr_dt", ssa=False,
-                 integrator="trapz", device=None, group=None):
+                 integrator="trapz", device=None, group=None, ebl=None):
         if scenario not in ("ssc", "ec_blr_dt"):
             raise ValueError("scenario must be 'ssc' or 'ec_blr_dt'")
         self.ne_kind, self.scenario, self.group = ne_kind, scenario, group
@@ -117,6 +117,12 @@ class FitSedBatch:
         self.n_nu = nu.size
         self.device = self.plans["synch"].device
         self.torch = self.plans["synch"].torch
+        # optional EBL attenuation (agnpy_b200.ebl.EBL): table resident on the device, applied to
+        # the summed SEDs of each shard in place with the per-vector redshifts
+        self.ebl = None
+        if ebl is not None:
+            dev = lambda a: self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+            self.ebl = dict(e=dev(ebl.energy_ref), z=dev(ebl.z_ref), v=dev(ebl.values_ref.T))
 
     def _local_components(self, models, lo, hi):
         return {name: plan._local(models[name][lo:hi]).clone() for name, plan in self.plans.items()}
@@ -139,6 +145,14 @@ class FitSedBatch:
             for name, plan in self.plans.items():
                 part = plan._local(models[name][lo:hi])
                 total = part.clone() if total is None else total.add_(part)
+            if self.ebl is not None:
+                z_dev = self.torch.from_numpy(np.ascontiguousarray(models["synch"]["z"][lo:hi])).to(self.device)
+                t, nu_dev = self.ebl, self.plans["synch"].nu
+                st = self.torch.cuda.current_stream(self.device).cuda_stream
+                _lib.check(_lib.lib().agnpy_b200_ebl_absorption(
+                    hi - lo, z_dev.data_ptr(), nu_dev.data_ptr(), self.n_nu, t["e"].data_ptr(),
+                    t["e"].numel(), t["z"].data_ptr(), t["z"].numel(), t["v"].data_ptr(), 1,
+                    total.data_ptr(), st), "agnpy_b200_ebl_absorption")
             return total
         return sharded_evaluate(local, index, self.n_nu, self.group, self.device)
 

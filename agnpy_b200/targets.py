@@ -16,13 +16,30 @@ lines_dictionary = {"Lyalpha": 1215.67, "Lybeta": 1025.72, "CIV": 1549.06, "MgII
                     "Hbeta": 4861.33, "Halpha": 6562.80}
 
 
+def _u_call(variant, tgt, r, blob, n_mu=50):
+    """u(r[, blob]) of one target through agnpy_b200_target_u (targets.py:202-218, 429-466,
+    516-543, 620-638); r keeps its shape, the result is a Quantity in erg cm-3"""
+    r_cm = strip(r, "cm", "r")
+    models = _lib.make_models(1)
+    _core.model_row(models, 0, tgt=tgt)
+    Gamma = None if blob is None else float(blob.Gamma)
+    out = _core.target_u_host(variant, models, np.ravel(r_cm), Gamma, n_mu)
+    return wrap(out[0].reshape(np.shape(r_cm)), "erg cm-3")
+
+
 class CMB:
-    """targets.py:154-169"""
+    """targets.py:154-183"""
 
     def __init__(self, z):
         T = 2.72548
         self.u_0 = (7.5657 * 1e-15 * np.power(T, 4)) * np.power(1 + z, 4) * u.Unit("erg cm-3")
         self.epsilon_0 = (2.7 * const.k_B * T / const.mec2) * (1 + z)
+
+    def u(self, blob=None):
+        """targets.py:171-183 (two flops: evaluated on the host)"""
+        if blob:
+            return self.u_0 * (np.power(blob.Gamma, 2) * (1 + np.power(blob.Beta, 2) / 3))
+        return self.u_0
 
 
 class PointSourceBehindJet:
@@ -30,6 +47,10 @@ class PointSourceBehindJet:
 
     def __init__(self, L_0, epsilon_0):
         self.L_0, self.epsilon_0 = L_0, epsilon_0
+
+    def u(self, r, blob=None):
+        """targets.py:202-218"""
+        return _u_call(_lib.EC_PS_BEHIND_JET, [self.epsilon_0, strip(self.L_0, "erg s-1", "L_0")], r, blob)
 
 
 class SSDisk:
@@ -76,6 +97,12 @@ class SSDisk:
         return self.evaluate_multi_T_bb_norm_sed(nu, z, self.L_disk, self.M_BH, self.m_dot, self.R_in,
                                                  self.R_out, d_L, mu_s)
 
+    def u(self, r, blob=None):
+        """targets.py:429-466"""
+        tgt = [strip(self.M_BH, "g", "M_BH"), strip(self.L_disk, "erg s-1", "L_disk"), float(self.eta),
+               strip(self.R_in, "cm", "R_in"), strip(self.R_out, "cm", "R_out")]
+        return _u_call(_lib.EC_SS_DISK, tgt, r, blob, n_mu=100)
+
 
 class SphericalShellBLR:
     """targets.py:469-497"""
@@ -86,6 +113,12 @@ class SphericalShellBLR:
         self.L_disk, self.xi_line, self.line, self.R_line = L_disk, xi_line, line, R_line
         lam_cm = lines_dictionary[line] * 1e-8
         self.epsilon_line = const.h * const.c / lam_cm / const.mec2
+
+    def u(self, r, blob=None):
+        """targets.py:516-543"""
+        tgt = [strip(self.L_disk, "erg s-1", "L_disk"), float(self.xi_line), self.epsilon_line,
+               strip(self.R_line, "cm", "R_line")]
+        return _u_call(_lib.EC_BLR, tgt, r, blob, n_mu=50)
 
 
 class RingDustTorus:
@@ -127,6 +160,12 @@ class RingDustTorus:
         """targets.py:612-618; d_L must be given (the reference derives it from z)"""
         L_dt = self.xi_dt * strip(self.L_disk, "erg s-1", "L_disk") * u.Unit("erg s-1")
         return self.evaluate_bb_norm_sed(nu, z, L_dt, self.T_dt, self.R_dt, d_L)
+
+    def u(self, r, blob=None):
+        """targets.py:620-638"""
+        tgt = [strip(self.L_disk, "erg s-1", "L_disk"), float(self.xi_dt), self.epsilon_dt,
+               strip(self.R_dt, "cm", "R_dt")]
+        return _u_call(_lib.EC_DT, tgt, r, blob)
 
 
 class Blob:

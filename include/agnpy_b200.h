@@ -215,6 +215,33 @@ int agnpy_b200_bb_sed_host(int variant, int n_models, const agnpy_model_t* model
                            const double* nu, int n_nu, const double* nu_norm, int n_norm, int n_R,
                            double* sed);
 
+/* ---- integral energy densities of the targets -------------------------------------------------
+ * replaces PointSourceBehindJet.u / SSDisk.u / SphericalShellBLR.u / RingDustTorus.u
+ *          agnpy/targets/targets.py:202-218, 429-466, 516-543, 620-638
+ * variant: AGNPY_EC_PS_BEHIND_JET, AGNPY_EC_SS_DISK, AGNPY_EC_BLR or AGNPY_EC_DT, with the same
+ * models[m].tgt layout as agnpy_b200_ec_sed (the trailing distance entry is ignored: r[n_r] is
+ * the array of distances along the jet axis, cm).  Gamma[n_models]: bulk Lorentz factors of the
+ * blobs for the comoving frame, or NULL for the stationary frame.  n_mu: size of the zenith grid
+ * (the reference uses 50 for the BLR, 100 for the disk; ignored otherwise).
+ * u is [n_models][n_r], erg cm-3. */
+int agnpy_b200_target_u(int variant, int n_models, const agnpy_model_t* models, const double* Gamma,
+                        const double* r, int n_r, int n_mu, double* u, void* stream);
+int agnpy_b200_target_u_host(int variant, int n_models, const agnpy_model_t* models,
+                             const double* Gamma, const double* r, int n_r, int n_mu, double* u);
+
+/* ---- EBL absorption ----------------------------------------------------------------------------
+ * replaces EBL.absorption   agnpy/absorption/ebl_absorption.py:59-73
+ * Bilinear interpolation of the table values[n_e][n_z] (energy_ref in keV ascending, z_ref
+ * ascending: the reference's `values_ref.T`) at (h nu, z[m]); NaN outside the table like the
+ * reference's RegularGridInterpolator(bounds_error=False).  multiply = 0: out[m][i] = absorption;
+ * multiply != 0: out[m][i] *= absorption (in place on a batch of SEDs).  out is [n_models][n_nu]. */
+int agnpy_b200_ebl_absorption(int n_models, const double* z, const double* nu, int n_nu,
+                              const double* energy_ref, int n_e, const double* z_ref, int n_z,
+                              const double* values, int multiply, double* out, void* stream);
+int agnpy_b200_ebl_absorption_host(int n_models, const double* z, const double* nu, int n_nu,
+                                   const double* energy_ref, int n_e, const double* z_ref, int n_z,
+                                   const double* values, int multiply, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -993,3 +993,134 @@ def ssc_electron_energy_loss_rate(gamma_eval, z, d_L, delta_D, B, R_b, ne_kind, 
         f_KN = np.where(b < 1e4, 1 / (1 + b) ** 1.5, (9 / (2 * b**2)) * (clipped_log(b) - 11 / 6))
     F_KN = trapz(f_KN * u_epsilon, epsilon, axis=1)
     return (4 / 3) * SIGMA_T * C_LIGHT * F_KN * gamma_eval**2
+
+
+# --------------------------------------------------------------------------
+# integral energy densities of the targets u(r[, blob]) and the
+# EBL absorption table.  `Gamma=None` is the stationary frame, a float the frame
+# comoving with a blob of that bulk Lorentz factor (Beta = sqrt(1 - 1/Gamma^2),
+# emission_regions/blob.py:134-136).
+# --------------------------------------------------------------------------
+def _beta(Gamma):
+    return np.sqrt(1 - 1 / np.power(Gamma, 2))
+
+
+def u_cmb(u_0, Gamma=None):
+    """targets.py:171-183"""
+    if Gamma:
+        return u_0 * np.power(Gamma, 2) * (1 + np.power(_beta(Gamma), 2) / 3)
+    return u_0
+
+
+def u_ps_behind_jet(L_0, r, Gamma=None):
+    """targets.py:202-218"""
+    r = np.asarray(r, dtype=float)
+    u_0 = L_0 / (4 * np.pi * C_LIGHT * np.power(r, 2))
+    if Gamma:
+        return u_0 / (np.power(Gamma, 2) * np.power(1 + _beta(Gamma), 2))
+    return u_0
+
+
+def u_ss_disk(M_BH, L_disk, eta, R_in, R_out, r, Gamma=None):
+    """targets.py:429-466 (R_in, R_out, r in cm)"""
+    r = np.atleast_1d(np.asarray(r, dtype=float))
+    R_g = G_NEWTON * M_BH / C_LIGHT**2
+    M_8 = M_BH / (1e8 * M_SUN)
+    L_Edd = 1.26 * 1e46 * M_8
+    l_Edd = L_disk / L_Edd
+    R_in_tilde, R_out_tilde = R_in / R_g, R_out / R_g
+    r_tilde = r / R_g
+    mu = disk_mu_from_r_tilde(R_in_tilde, R_out_tilde, r_tilde)
+    prefactor = 3 * l_Edd * L_Edd * R_g / (8 * np.pi * C_LIGHT * eta * np.power(r, 3))
+    integrand = 1 / mu * np.power(np.power(mu, -2) - 1, -3 / 2) * disk_phi_disk_mu(
+        mu, R_in_tilde, r_tilde)
+    if Gamma:
+        Beta = _beta(Gamma)
+        mu_prime = (mu - Beta) / (1 - Beta * mu)
+        integrand_prefactor = 1 / (np.power(Gamma, 6) * np.power(1 - Beta * mu, 2)
+                                   * np.power(1 + Beta * mu_prime, 4))
+        integrand = integrand * integrand_prefactor
+    integral = np.trapezoid(integrand, mu, axis=0)
+    return prefactor * integral
+
+
+def u_blr(L_disk, xi_line, R_line, r, Gamma=None):
+    """targets.py:516-543"""
+    r = np.atleast_1d(np.asarray(r, dtype=float))
+    mu = np.linspace(-1, 1)
+    _mu = mu.reshape(mu.size, 1)
+    _r = r.reshape(1, r.size)
+    _x2 = np.power(_r, 2) + np.power(R_line, 2) - 2 * _r * R_line * _mu
+    prefactor = xi_line * L_disk / (8 * np.pi * C_LIGHT)
+    integrand = 1 / _x2
+    if Gamma:
+        _mu_star = np.sqrt(1 - np.power(R_line, 2) / _x2 * (1 - np.power(_mu, 2)))
+        integrand = integrand * (np.power(Gamma, 2) * np.power(1 - _beta(Gamma) * _mu_star, 2))
+    integral = np.trapezoid(integrand, mu, axis=0)
+    return prefactor * integral
+
+
+def u_dt(L_disk, xi_dt, R_dt, r, Gamma=None):
+    """targets.py:620-638"""
+    r = np.asarray(r, dtype=float)
+    x2 = np.power(R_dt, 2) + np.power(r, 2)
+    x = np.sqrt(x2)
+    integral = xi_dt * L_disk / (4 * np.pi * C_LIGHT * x2)
+    if Gamma:
+        mu = r / x
+        integral = integral * np.power(Gamma * (1 - _beta(Gamma) * mu), 2)
+    return integral
+
+
+KEV_ERG = 1.602176634e-9  # 1 keV in erg (CODATA 2018, exact)
+
+
+def read_ebl_fits(path):
+    """absorption/ebl_absorption.py:44-57 without astropy.io.fits: the three binary tables of
+    the XSPEC-style table model (big-endian float32), returned as the reference stores them:
+    energy_ref [keV] = sqrt(ENERG_LO * ENERG_HI), z_ref = PARAMVAL, values_ref = INTPSPEC
+    (float32 arrays; the duplicated z = 1.001 row of franceschini_2008 is NOT removed here)."""
+    import gzip
+    raw = gzip.open(path, "rb").read() if str(path).endswith(".gz") else open(path, "rb").read()
+    pos, tables = 0, {}
+    while pos < len(raw):
+        hdr = {}
+        done = False
+        while not done:
+            block = raw[pos:pos + 2880]
+            pos += 2880
+            for i in range(0, 2880, 80):
+                card = block[i:i + 80].decode("ascii", "replace")
+                if card[:8].strip() == "END":
+                    done = True
+                    break
+                if card[8:10] == "= ":
+                    hdr[card[:8].strip()] = card[10:].split("/")[0].strip().strip("'").strip()
+        naxis = int(hdr.get("NAXIS", "0"))
+        size = 0
+        if naxis:
+            size = abs(int(hdr["BITPIX"])) // 8
+            for a in range(1, naxis + 1):
+                size *= int(hdr[f"NAXIS{a}"])
+            size += int(hdr.get("PCOUNT", "0"))
+        data = raw[pos:pos + size]
+        pos += (size + 2879) // 2880 * 2880
+        if hdr.get("XTENSION") == "BINTABLE":
+            rows, width = int(hdr["NAXIS2"]), int(hdr["NAXIS1"])
+            tables[hdr.get("EXTNAME")] = np.frombuffer(data[:rows * width], dtype=">f4").reshape(
+                rows, width // 4) if hdr.get("EXTNAME") != "PARAMETERS" else None
+    en = tables["ENERGIES"].astype(np.float32)
+    sp = tables["SPECTRA"].astype(np.float32)
+    energy_ref = np.sqrt(en[:, 0] * en[:, 1])
+    return energy_ref, sp[:, 0].copy(), sp[:, 1:].copy()
+
+
+def ebl_absorption(nu, z, energy_ref, z_ref, values_ref):
+    """absorption/ebl_absorption.py:59-73: scipy RegularGridInterpolator, linear,
+    bounds_error=False (NaN outside the table)"""
+    from scipy.interpolate import RegularGridInterpolator
+    model = RegularGridInterpolator(points=(energy_ref, z_ref), values=values_ref.T, method="linear",
+                                    bounds_error=False)
+    energy = H_PLANCK * np.asarray(nu, dtype=float) / KEV_ERG
+    z_array = np.full_like(energy, z)
+    return model(np.vstack([energy, z_array]).T)
