@@ -232,3 +232,79 @@ def test_unusual_gamma_grids(grid):
         ref = orc.ssc_sed_flux(c1["nu"], c1["z"], c1["d_L"], c1["delta_D"], c1["B"], c1["R_b"], c1["ne_kind"],
                                c1["ne_args"], integrator=integ, gamma=g1)
         assert_parity(got.value, ref, what=f"ssc {grid} {integ}")
+
+
+# ---- the np.trapz polynomial EC path: frequency chunks, sorted pair segments, plan switches ------
+@pytest.mark.parametrize("l_nu", ["1", "3", "8"])
+@pytest.mark.parametrize("order", ["ascending", "descending", "shuffled"])
+def test_ec_poly_frequency_chunks(monkeypatch, l_nu, order):
+    """a block walks L_nu frequencies and advances its index window from one to the next:
+    any chunk length and any frequency order must give the single-frequency result"""
+    c = cases.case_c2(n_nu=29, r=3e17, n_gamma=150, n_mu=40, n_phi=24)   # 960 pairs, ragged chunks
+    nu = c["nu"]
+    if order == "descending":
+        nu = nu[::-1].copy()
+    elif order == "shuffled":
+        nu = np.random.default_rng(11).permutation(nu)
+    c = dict(c, nu=nu)
+    monkeypatch.setenv("AGNPY_B200_EC_LNU", l_nu)
+    got = blr_call(c)
+    assert_parity(got, cases.ORACLE_EC["blr"](c), what=f"L_nu={l_nu} {order}")
+    monkeypatch.setenv("AGNPY_B200_EC_LNU", "1")
+    np.testing.assert_array_equal(blr_call(c), got)     # chunking never changes a bit
+
+
+@pytest.mark.parametrize("n_mu,n_phi", [(16, 32), (17, 32), (31, 17), (70, 31), (130, 67)])
+def test_ec_poly_pair_counts(monkeypatch, n_mu, n_phi):
+    """pair counts around the plan switches: 512 (v4 kernel below, polynomial path from there on),
+    one partly filled 1024-pair sort segment, several segments, J = 4 and J = 8 tiles"""
+    monkeypatch.setenv("AGNPY_B200_EC_LNU", "4")
+    c = cases.case_c2(n_nu=9, r=2e17, n_gamma=90, n_mu=n_mu, n_phi=n_phi)
+    assert_parity(blr_call(c), cases.ORACLE_EC["blr"](c), what=f"{n_mu}x{n_phi} pairs")
+
+
+def test_ec_poly_off_axis_strong_phi_dependence(monkeypatch):
+    """mu_s far from 1: c varies strongly with phi, the sorted order interleaves the mu rows"""
+    monkeypatch.setenv("AGNPY_B200_EC_LNU", "8")
+    c = cases.case_c2(n_nu=17, r=1e18, n_gamma=120, n_mu=48, n_phi=40)
+    c = dict(c, mu_s=0.3)
+    assert_parity(blr_call(c), cases.ORACLE_EC["blr"](c), what="mu_s = 0.3")
+
+
+def test_ec_poly_long_gamma_grid(monkeypatch):
+    """1000 gamma points: 32 KB rows, one frequency per block whatever the knob asks for"""
+    monkeypatch.setenv("AGNPY_B200_EC_LNU", "8")
+    c = cases.case_c2(n_nu=5, r=5e17, n_gamma=1000, n_mu=24, n_phi=24)
+    assert_parity(blr_call(c), cases.ORACLE_EC["blr"](c), what="n_gamma = 1000")
+
+
+# ---- the np.trapz SSC path: gamma slots, seed grids that are not log-uniform ----------------------
+@pytest.mark.parametrize("n_gamma", [2, 31, 33, 300])
+def test_ssc_gamma_slot_counts(n_gamma):
+    c = cases.case_c1(n_nu=23)
+    gamma = np.logspace(1, 6, n_gamma)
+    got = ab.SynchrotronSelfCompton.evaluate_sed_flux(
+        c["nu"] * u.Hz, c["z"], c["d_L"] * u.cm, c["delta_D"], c["B"] * u.G, c["R_b"] * u.cm,
+        ne_obj(c["ne_kind"], c["ne_args"]), *q_args(c["ne_args"]), gamma=gamma).value
+    ref = orc.ssc_sed_flux(c["nu"], c["z"], c["d_L"], c["delta_D"], c["B"], c["R_b"], c["ne_kind"],
+                           c["ne_args"], gamma=gamma)
+    assert_parity(got, ref, what=f"ssc n_gamma={n_gamma}")
+
+
+def test_ssc_batch_on_irregular_seed_grid():
+    """the seed-range search starts from a log-uniform guess; an irregular seed grid must fall back
+    to the plain search and still match (batched entry point, custom nu_seed)"""
+    from agnpy_b200 import _core
+    from agnpy_b200.batch import SedBatch
+    c = cases.case_c1(n_nu=19)
+    rng = np.random.default_rng(5)
+    nu_seed = np.sort(10 ** rng.uniform(5, 30, 137))
+    models = _lib.make_models(3)
+    for i in range(3):
+        _core.model_row(models, i, z=c["z"], d_L=c["d_L"], delta_D=c["delta_D"] * (1 + i), B=c["B"],
+                        R_b=c["R_b"], ne=list(c["ne_args"]) + [0, 0])
+    got = SedBatch("ssc", c["nu"], c["ne_kind"], gamma=c["gamma"], nu_seed=nu_seed)(models)
+    for i in range(3):
+        ref = orc.ssc_sed_flux(c["nu"], c["z"], c["d_L"], c["delta_D"] * (1 + i), c["B"], c["R_b"],
+                               c["ne_kind"], c["ne_args"], gamma=c["gamma"], nu_seed=nu_seed)
+        assert_parity(got[i], ref, what=f"irregular seed grid, model {i}")
