@@ -535,16 +535,22 @@ __global__ void __launch_bounds__(256) ssc_trapz_kernel(
         }
         const int JA = __reduce_min_sync(0xffffffffu, ja);
         const int JB = __reduce_max_sync(0xffffffffu, jb);
+        // every lane evaluates every seed of the warp's band (a warp pays for the instruction
+        // whether or not a lane is predicated off); a lane outside its own band adds with weight 0.
+        // F stays finite there (h2 = 0 or a finite q), so 0 * F = 0 exactly.
+        const double4* p = sj + JA;
+        // t in [ja - JA, jb - JA]  <=>  (unsigned)(t - rel_lo) <= rel_n;  empty band: never true
+        const unsigned rel_lo = jb >= ja ? (unsigned)(ja - JA) : 0x80000000u;
+        const unsigned rel_n = jb >= ja ? (unsigned)(jb - ja) : 0u;
 #pragma unroll 4
-        for (int j = JA; j <= JB; ++j) {
-            const double4 c = sj[j];  // warp-uniform: {1/eps_j, -ln eps_j, w_j U_j, eps_j}
-            if (j >= ja && j <= jb) {
-                const double sq = h2 * c.x;            // 2q
-                const double lq = lh + c.y;            // ln q
-                const double t = fma(-0.5, sq, 1.0);   // 1 - q
-                const double F = fma(sq, lq, t * (c1 + sq));
-                acc = fma(c.z, F, acc);
-            }
+        for (int t = 0; t <= JB - JA; ++t) {
+            const double4 c = p[t];  // warp-uniform: {1/eps_j, -ln eps_j, w_j U_j, eps_j}
+            const double wU = ((unsigned)t - rel_lo <= rel_n) ? c.z : 0.0;
+            const double sq = h2 * c.x;             // 2q
+            const double lq = lh + c.y;             // ln q
+            const double om = fma(-0.5, sq, 1.0);   // 1 - q
+            const double F = fma(sq, lq, om * (c1 + sq));
+            acc = fma(wU, F, acc);
         }
         total = fma(fw, acc, total);
     }
