@@ -463,7 +463,12 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
 // positive doubles (integer pipe, not FP64).  The guard band around c (|hi32(G) - hi32(c)| <= 3,
 // i.e. >= 1.4e-6 relative) and the exact re-decision inside it are those of the v4 kernel.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int ec_row_words(int n_gamma) { return (4 * n_gamma + 2 + 1) & ~1; }
+// row of one (nu, model): {Q,R}[n + kRowPad] (the pad entries are zero: the unrolled gamma loop may run
+// up to 3 steps past the last electron index), G[n], SP[n + 1], {ill_lo, ill_hi}; even word count
+constexpr int kRowPad = 4;
+__host__ __device__ __forceinline__ int ec_row_words(int n_gamma) {
+    return (2 * (n_gamma + kRowPad) + 2 * n_gamma + 2 + 1) & ~1;
+}
 
 // Second table launch (1024 threads); the block role follows from blockIdx.x:
 //   [0, nSeg)            pair table: one sorted segment per block (from the unsorted values)
@@ -481,11 +486,12 @@ __device__ __forceinline__ void ec_poly_row_role(
     const double* g_f = gt + (size_t)m * 5 * n_gamma + n_gamma;
     double* row = rows + ((size_t)m * n_nu + i) * ec_row_words(n_gamma);
     double2* r_QR = reinterpret_cast<double2*>(row);
-    double* r_G = row + 2 * n_gamma;
+    double* r_G = row + 2 * (n_gamma + kRowPad);
     double* r_SP = r_G + n_gamma;
     const int klo = hull[2 * m], khi = hull[2 * m + 1];
     // EC uses nu_to_epsilon_prime(nu, z) without the Doppler factor (external_compton.py:123)
     const double eps_s = nu_to_eps(nu[i], models[m].z, 1.0);
+    if (lane < kRowPad) r_QR[n_gamma + lane] = make_double2(0.0, 0.0);
     double carry = 0.0;
     int ill_lo = n_gamma, ill_hi = 0;
     for (int base = ((n_gamma - 1) >> 5) << 5; base >= 0; base -= 32) {
@@ -498,7 +504,7 @@ __device__ __forceinline__ void ec_poly_row_role(
             const double G = (y > 0.0) ? eps_s / ((g * g) * y) : INFINITY;
             const double wf = g_f[k];
             const bool live = k >= klo && k <= khi && G < kFmax;
-            const double wG = wf * G;
+            const double wG = live ? wf * G : 0.0;  // exactly 0 outside the electron range
             r_QR[k] = make_double2(wG * G, -2.0 * wG);
             r_G[k] = G;
             P = live ? wf * A : 0.0;
@@ -639,8 +645,8 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
     }
 
     double b[J], b2[J];
-    long long ci[J];  // bits of c (> 0); <= 0 marks a pair that never contributes
-    long long cmax = -1, cmin = LLONG_MAX;  // over the live pairs of the warp
+    int hc[J];  // high word of c (> 0); -1 marks a pair that never contributes
+    long long cmax = -1, cmin = LLONG_MAX;  // bits of c over the live pairs of the warp
 #pragma unroll
     for (int jj = 0; jj < J; ++jj) {
         const int j = jbase + jj;
@@ -648,8 +654,9 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
         b[jj] = valid ? a_b[j] : 0.0;
         b2[jj] = b[jj] * b[jj];
         const double c = valid ? a_c[j] : -1.0;
-        ci[jj] = (c > 0.0) ? __double_as_longlong(c) : -1LL;
-        if (ci[jj] > 0) { cmax = max(cmax, ci[jj]); cmin = min(cmin, ci[jj]); }
+        const long long ci = (c > 0.0) ? __double_as_longlong(c) : -1LL;
+        hc[jj] = (int)(ci >> 32);
+        if (ci > 0) { cmax = max(cmax, ci); cmin = min(cmin, ci); }
     }
     cmax = warp_max_ll(cmax);
     cmin = warp_min_ll(cmin);
@@ -660,9 +667,9 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
         mbar_wait(bars + (i - i0), 0);
         const double* s_row = sh + (size_t)(i - i0) * row_words;
         const double2* s_QR = reinterpret_cast<const double2*>(s_row);
-        const long long* s_Gi = reinterpret_cast<const long long*>(s_row + 2 * n_gamma);
-        const int* s_Gh = reinterpret_cast<const int*>(s_row + 2 * n_gamma);  // [2k+1] = high word
-        const double* s_SP = s_row + 3 * n_gamma;
+        const long long* s_Gi = reinterpret_cast<const long long*>(s_row + 2 * (n_gamma + kRowPad));
+        const int* s_Gh = reinterpret_cast<const int*>(s_Gi);  // [2k+1] = high word
+        const double* s_SP = s_row + 2 * (n_gamma + kRowPad) + n_gamma;
         double thread_sum = 0.0;
         if (warp_live) {
             // warp-uniform index window [wlo, whi]: every live pair's first unmasked index lies in it
@@ -673,14 +680,16 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
                 wlo = ec_search_step(s_Gi, n_gamma, cmax, wlo);
                 whi = ec_search_step(s_Gi, n_gamma, cmin, whi);
             }
-            // per pair: lo = wlo + #{k in [wlo, whi) : G_k > c}   (G descending: a prefix count)
+            // per pair: lo = wlo + #{k in [wlo, whi) : G_k > c}   (G descending: a prefix count).
+            // The count compares high words only; a tie there lands inside the guard band below
+            // and is re-decided exactly.
             int lo[J];
 #pragma unroll
             for (int jj = 0; jj < J; ++jj) lo[jj] = wlo;
             for (int k = wlo; k < whi; ++k) {
-                const long long g = s_Gi[k];
+                const int gh = s_Gh[2 * k + 1];
 #pragma unroll
-                for (int jj = 0; jj < J; ++jj) lo[jj] += (g > ci[jj]) ? 1 : 0;
+                for (int jj = 0; jj < J; ++jj) lo[jj] += (gh > hc[jj]) ? 1 : 0;
             }
             // guard band: a neighbour of the index within ~1e-6 of c, an ill-conditioned G in the
             // window, or a non-finite c -> decide that pair with the reference's own formula
@@ -691,11 +700,10 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
 #pragma unroll
             for (int jj = 0; jj < J; ++jj) {
                 const int k = lo[jj];
-                const int hc = (int)(ci[jj] >> 32);
                 const int ha = s_Gh[2 * min(k, n_gamma - 1) + 1], hb = s_Gh[2 * max(k - 1, 0) + 1];
-                const bool d = (k < n_gamma && abs(ha - hc) <= 3) || (k > 0 && abs(hb - hc) <= 3) ||
-                               w_ill || hc >= 0x7ff00000;
-                if (ci[jj] > 0) {
+                const bool d = (k < n_gamma && abs(ha - hc[jj]) <= 3) || (k > 0 && abs(hb - hc[jj]) <= 3) ||
+                               w_ill || hc[jj] >= 0x7ff00000;
+                if (hc[jj] >= 0) {
                     if (d) doubt |= 1u << jj;
                     tmin = min(tmin, k);
                     tmax = max(tmax, k);
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
                     if (doubt & (1u << jj))
                         lo[jj] = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc, jbase + jj, nu[i],
                                                        models[m].z);
-                    if (ci[jj] > 0) { tmin = min(tmin, lo[jj]); tmax = max(tmax, lo[jj]); }
+                    if (hc[jj] >= 0) { tmin = min(tmin, lo[jj]); tmax = max(tmax, lo[jj]); }
                 }
             }
             double acc[J];
@@ -735,18 +743,26 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
                 }
             }
             // phase 2: every live lane is above its gamma_min -> 2 DFMA per integrand point
-            // (the table entry of step k+1 is fetched before the 2J DFMAs of step k issue, so
-            // the shared-memory latency hides behind them even when the warp runs alone)
-            if (kmid <= khi) {
-                double2 qr = s_QR[kmid];
-                for (int k = kmid; k <= khi; ++k) {
-                    const double2 nx = s_QR[min(k + 1, khi)];
+            // four gamma steps per trip and no remainder loop: the row carries kRowPad zero entries
+            // after the last index, so running past khi adds exact zeros
+            for (int k = kmid; k <= khi; k += 4) {
+                const double2 q0 = s_QR[k], q1 = s_QR[k + 1], q2 = s_QR[k + 2], q3 = s_QR[k + 3];
 #pragma unroll
-                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.x, b2[jj], acc[jj]);
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q0.x, b2[jj], acc[jj]);
 #pragma unroll
-                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.y, b[jj], acc[jj]);
-                    qr = nx;
-                }
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q0.y, b[jj], acc[jj]);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q1.x, b2[jj], acc[jj]);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q1.y, b[jj], acc[jj]);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q2.x, b2[jj], acc[jj]);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q2.y, b[jj], acc[jj]);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q3.x, b2[jj], acc[jj]);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q3.y, b[jj], acc[jj]);
             }
 #pragma unroll
             for (int jj = 0; jj < J; ++jj) {
