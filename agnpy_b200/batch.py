@@ -67,15 +67,19 @@ def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu"):
     return out[:n]
 
 
-def nu_slice(n_nu, world_size, rank):
-    """[lo, hi) of the frequencies owned by `rank` and the padded per-rank count (config 4:
-    the nu grid is sharded, every other grid is replicated)"""
-    return local_slice(n_nu, world_size, rank)
+def nu_indices(n_nu, world_size, rank):
+    """indices of the frequencies owned by `rank` and the padded per-rank count (config 4: the nu
+    grid is sharded, every other grid is replicated).  Round-robin, not contiguous: the cost of a
+    frequency falls steeply along the grid (fewer and fewer gamma points stay unmasked towards the
+    kinematic limit), so contiguous slices would leave the last ranks idle."""
+    per_rank = -(-n_nu // world_size)
+    return np.arange(rank, n_nu, world_size), per_rank
 
 
 def nu_sharded_evaluate(local_compute, nu, n_models, group=None, device="cpu"):
-    """Frequency sharding: `local_compute(nu[lo:hi]) -> tensor [n_models, hi-lo]` on this rank's
-    slice of the frequency grid, then ONE all-gather; returns [n_models, n_nu] on every rank."""
+    """Frequency sharding: `local_compute(nu[idx]) -> tensor [n_models, len(idx)]` on this rank's
+    frequencies (idx = rank, rank + world, ...), then ONE all-gather; returns [n_models, n_nu] on
+    every rank."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -83,12 +87,14 @@ def nu_sharded_evaluate(local_compute, nu, n_models, group=None, device="cpu"):
         return local_compute(nu)
     rank = dist.get_rank(group)
     n = len(nu)
-    lo, hi, per_rank = nu_slice(n, world, rank)
+    idx, per_rank = nu_indices(n, world, rank)
     block = torch.zeros(per_rank, n_models, dtype=torch.float64, device=device)  # [nu, model]
-    if hi > lo:
-        block[: hi - lo] = local_compute(nu[lo:hi]).transpose(0, 1)
+    if idx.size:
+        block[: idx.size] = local_compute(nu[idx]).transpose(0, 1)
     out = torch.empty(world * per_rank, n_models, dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(out, block, group=group)
+    # out[r * per_rank + j] is frequency j * world + r: undo the interleave
+    out = out.view(world, per_rank, n_models).transpose(0, 1).reshape(world * per_rank, n_models)
     return out[:n].transpose(0, 1).contiguous()
 
 
@@ -118,9 +124,9 @@ class SedBatch:
         if shard == "nu":  # this rank keeps only its slice of the frequency grid on the device
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
-                lo, hi, _ = nu_slice(self.nu_full.size, dist.get_world_size(group), dist.get_rank(group))
-                nu = self.nu_full[lo:hi] if hi > lo else self.nu_full[:1]
-                self._nu_empty = hi <= lo
+                idx, _ = nu_indices(self.nu_full.size, dist.get_world_size(group), dist.get_rank(group))
+                nu = self.nu_full[idx] if idx.size else self.nu_full[:1]
+                self._nu_empty = idx.size == 0
             else:
                 self._nu_empty = False
         self.ne_kind = _NE_KINDS[ne_kind] if isinstance(ne_kind, str) else int(ne_kind)
