@@ -24,6 +24,12 @@ Parity pinning (see tests/test_oracle_*.py and tests/golden/make_golden.py):
   * `tau_ss_disk`: PARITY UNPINNED by the reference (its only test is
     `assert True`, agnpy/absorption/tests/test_absorption.py:70); it is pinned
     here only through the shared `sigma`/`cos_psi` pieces.
+  * target energy densities `u_*`: pinned by the reference's
+    known-answer vectors for the CMB, point source, BLR and torus in both frames
+    (agnpy/targets/tests/test_targets.py:50-90, 223-372); `u_ss_disk`: PARITY
+    UNPINNED (the reference has no test of SSDisk.u).  `ebl_absorption` calls the
+    same scipy RegularGridInterpolator as the reference on the reference's own
+    table file (tests/golden/reference_data/ebl_models/frd_abs.fits.gz).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).
