@@ -479,21 +479,33 @@ __device__ __forceinline__ int first_true_near(int j, int n, Pred pred) {
 }
 
 // block = NW warps (blockDim.x / 32): warp w takes the gamma slots w, w + NW, ...
+// The per-seed constants of the model are staged in shared memory ({1/eps, -ln eps} as 16-byte
+// pairs, w U separately: 24 bytes per seed) so that the range searches and the seed walk read
+// them as shared-memory broadcasts.
 __global__ void __launch_bounds__(256) ssc_trapz_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu, int n_gamma,
     const double4* __restrict__ gk_all, const double4* __restrict__ sj_all, int n_seed,
     double* __restrict__ out) {
+    extern __shared__ __align__(16) double s_seed[];  // double2 q[n_seed], double wU[n_seed]
     __shared__ double s_part[8];
     const int m = blockIdx.y, i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_warps = blockDim.x >> 5;
     const agnpy_model_t& M = models[m];
     const double4* gk = gk_all + (size_t)m * n_gamma;
     const double4* sj = sj_all + (size_t)m * n_seed;
+    double2* s_q = reinterpret_cast<double2*>(s_seed);
+    double* s_w = s_seed + 2 * (size_t)n_seed;
+    for (int j = threadIdx.x; j < n_seed; j += blockDim.x) {
+        const double4 c = sj[j];
+        s_q[j] = make_double2(c.x, c.y);
+        s_w[j] = c.z;
+    }
+    __syncthreads();
     const double eps_s = nu_to_eps(nu[i], M.z, M.delta_D);
     const double l_eps_s = log(eps_s);
     // ln eps_j ~ l0 + j dl on a log-uniform seed grid: starting guess of the range searches
-    const double l0 = -sj[0].y;
-    const double inv_dl = (double)(n_seed - 1) / (-sj[n_seed - 1].y - l0);
+    const double l0 = -s_q[0].y;
+    const double inv_dl = (double)(n_seed - 1) / (-s_q[n_seed - 1].y - l0);
     double total = 0.0;
     for (int k0 = 32 * warp; k0 < n_gamma; k0 += 32 * n_warps) {
         const int k = k0 + lane;
@@ -513,20 +525,20 @@ __global__ void __launch_bounds__(256) ssc_trapz_kernel(
                 c1 = 1.0 + 0.5 * (v * v) / (1.0 + v);
                 // candidates: q <= 1+guard and q >= q_min (1-guard); q(j) = h/eps_j falls with j
                 int a = first_true_near((int)ceil((lh - l0) * inv_dl), n_seed,
-                                        [&](int j) { return h * sj[j].x <= 1.0 + kGuard; });
+                                        [&](int j) { return h * s_q[j].x <= 1.0 + kGuard; });
                 int b = first_true_near((int)ceil((lh + G.z - l0) * inv_dl), n_seed,
-                                        [&](int j) { return h * sj[j].x < q_out_lo; }) - 1;
+                                        [&](int j) { return h * s_q[j].x < q_out_lo; }) - 1;
                 // shrink to the surely-inside range; what is cut off is decided exactly
-                while (a <= b && !(h * sj[a].x <= 1.0 - kGuard)) {
+                while (a <= b && !(h * s_q[a].x <= 1.0 - kGuard)) {
                     bool in;
                     double F = Fc_exact(G.x, sj[a].w, eps_s, in);
-                    if (in) acc = fma(sj[a].z, F, acc);
+                    if (in) acc = fma(s_w[a], F, acc);
                     ++a;
                 }
-                while (b >= a && !(h * sj[b].x >= q_in_lo)) {
+                while (b >= a && !(h * s_q[b].x >= q_in_lo)) {
                     bool in;
                     double F = Fc_exact(G.x, sj[b].w, eps_s, in);
-                    if (in) acc = fma(sj[b].z, F, acc);
+                    if (in) acc = fma(s_w[b], F, acc);
                     --b;
                 }
                 ja = a;
@@ -538,14 +550,15 @@ __global__ void __launch_bounds__(256) ssc_trapz_kernel(
         // every lane evaluates every seed of the warp's band (a warp pays for the instruction
         // whether or not a lane is predicated off); a lane outside its own band adds with weight 0.
         // F stays finite there (h2 = 0 or a finite q), so 0 * F = 0 exactly.
-        const double4* p = sj + JA;
+        const double2* pq = s_q + JA;
+        const double* pw = s_w + JA;
         // t in [ja - JA, jb - JA]  <=>  (unsigned)(t - rel_lo) <= rel_n;  empty band: never true
         const unsigned rel_lo = jb >= ja ? (unsigned)(ja - JA) : 0x80000000u;
         const unsigned rel_n = jb >= ja ? (unsigned)(jb - ja) : 0u;
 #pragma unroll 4
         for (int t = 0; t <= JB - JA; ++t) {
-            const double4 c = p[t];  // warp-uniform: {1/eps_j, -ln eps_j, w_j U_j, eps_j}
-            const double wU = ((unsigned)t - rel_lo <= rel_n) ? c.z : 0.0;
+            const double2 c = pq[t];  // warp-uniform: {1/eps_j, -ln eps_j}
+            const double wU = ((unsigned)t - rel_lo <= rel_n) ? pw[t] : 0.0;
             const double sq = h2 * c.x;             // 2q
             const double lq = lh + c.y;             // ln q
             const double om = fma(-0.5, sq, 1.0);   // 1 - q
@@ -586,7 +599,13 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
         // of a row over up to 8 warps (latency of a single call)
         int slots = (n_gamma + 31) / 32, nw = 1;
         while (nw < 8 && nw < slots && (long long)n_nu * n_models * nw < 4096) nw <<= 1;
-        ssc_trapz_kernel<<<grid, 32 * nw, 0, stream>>>(models, nu, n_nu, n_gamma, gk, sj, n_seed, out);
+        const size_t smem_seed = 24 * (size_t)n_seed;
+        if (smem_seed > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_seed too large for the SSC kernel");
+        if (smem_seed > 48 * 1024)
+            cudaFuncSetAttribute(ssc_trapz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_seed);
+        ssc_trapz_kernel<<<grid, 32 * nw, smem_seed, stream>>>(models, nu, n_nu, n_gamma, gk, sj, n_seed,
+                                                              out);
         timing_end(stream);
         note_launch();
         return AGNPY_OK;
