@@ -21,7 +21,7 @@ black body of the disk and the normalised black body of the torus (sherpa_wrappe
 import numpy as np
 
 from . import _lib, constants as const, grids
-from .batch import SedBatch, sharded_evaluate
+from .batch import SedBatch, sharded_evaluate  # GraphedSum is imported lazily in graphed()
 
 # position (from the end of the spectral block) of the log10-scaled Lorentz factors besides
 # gamma_min / gamma_max, sherpa_wrapper.py:41-48
@@ -136,11 +136,15 @@ class FitSedBatch:
         return out
 
     def evaluate_device(self, pars, d_L):
-        models = build_models(pars, d_L, self.ne_kind, self.scenario)
-        index = np.arange(len(models["synch"]))
+        pars = np.atleast_2d(np.asarray(pars, dtype=np.float64))
+        d_L = np.broadcast_to(np.asarray(d_L, dtype=np.float64), (pars.shape[0],))
+        index = np.arange(pars.shape[0])
 
         def local(idx):
+            # only this rank's shard of the parameter table is turned into model rows
             lo, hi = int(idx[0]), int(idx[-1]) + 1
+            models = build_models(pars[lo:hi], d_L[lo:hi], self.ne_kind, self.scenario)
+            lo, hi = 0, hi - lo
             total = None
             for name, plan in self.plans.items():
                 part = plan._local(models[name][lo:hi])
@@ -161,3 +165,16 @@ class FitSedBatch:
             out = self.evaluate_device(pars, d_L)
             host = out.cpu()
         return host.numpy()
+
+    def graphed(self, n_vectors):
+        """the same model for a FIXED number of parameter vectors on this GPU, as one CUDA graph
+        (agnpy_b200.batch.GraphedSum): `g = model.graphed(32); sed = g(pars, d_L)` with pars of
+        shape [32, n_par].  Meant for the small batches of an optimiser or a sampler step, which are
+        launch-bound; results are bit-identical to `model(pars, d_L)`.  Not sharded."""
+        from .batch import GraphedSum
+        graph = GraphedSum(self.plans, n_vectors, self.ebl)
+
+        def call(pars, d_L):
+            return graph(build_models(pars, d_L, self.ne_kind, self.scenario))
+        call.graph = graph
+        return call
