@@ -129,26 +129,37 @@ __device__ __forceinline__ double trapz_weight(const double* x, int k, int n) {
     return (hi - lo) * 0.5;
 }
 
-// one interval of utils/math.py:55-119 (trapz_loglog); ly_* are clipped logs of y_*
+// one interval of utils/math.py:55-119 (trapz_loglog); ly_* are clipped logs of y_*.
+// m is the slope of the power law through both end points, so (x_up/x_lo)^m is y_up/y_lo by
+// construction and  y_lo/(m+1) (x_up (x_up/x_lo)^m - x_lo) = (x_up y_up - x_lo y_lo)/(m+1):
+// no pow / exp per interval.  (The reference evaluates the power numerically; the two agree to
+// ~|m ln(x_up/x_lo)| ulp.)  The identity needs the logs of the values themselves, so a y
+// that the reference clips (below the smallest normal double) keeps the literal formula.
 __device__ __forceinline__ double loglog_interval(double x_lo, double x_up, double y_lo,
                                                   double y_up, double ly_lo, double ly_up) {
     if (y_lo == 0.0 || y_up == 0.0 || x_lo == x_up) return 0.0;  // :112-117
     double m = (ly_lo - ly_up) / (clipped_log(x_lo) - clipped_log(x_up));  // :104
     double m1 = m + 1.0;
-    if (fabs(m1) > 1e-10)  // :106-110
+    if (fabs(m1) > 1e-10) {  // :106-110
+        if (fabs(y_lo) >= kTiny && fabs(y_up) >= kTiny && y_lo > 0.0 && y_up > 0.0)
+            return (x_up * y_up - x_lo * y_lo) / m1;
         return y_lo / m1 * (x_up * pow(x_up / x_lo, m) - x_lo);
+    }
     return x_lo * y_lo * clipped_log(x_up / x_lo);
 }
 
 // same interval with the per-interval constants precomputed: inv_dlx = 1/(ln x_lo - ln x_up),
-// lr = ln(x_up/x_lo); pow(r, m) is evaluated as exp(m*lr)
+// lr = ln(x_up/x_lo)
 __device__ __forceinline__ double loglog_interval_pre(double x_lo, double x_up, double inv_dlx,
                                                       double lr, double y_lo, double y_up,
                                                       double ly_lo, double ly_up) {
     if (y_lo == 0.0 || y_up == 0.0 || x_lo == x_up) return 0.0;
     double m = (ly_lo - ly_up) * inv_dlx;
     double m1 = m + 1.0;
-    if (fabs(m1) > 1e-10) return y_lo / m1 * (x_up * exp(m * lr) - x_lo);
+    if (fabs(m1) > 1e-10) {
+        if (y_lo >= kTiny && y_up >= kTiny) return (x_up * y_up - x_lo * y_lo) / m1;
+        return y_lo / m1 * (x_up * exp(m * lr) - x_lo);
+    }
     return x_lo * y_lo * lr;
 }
 
