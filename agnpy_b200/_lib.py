@@ -15,6 +15,7 @@ LIB_PATH = _PKG / "libagnpy_b200.so"
 NE_POWERLAW, NE_BROKEN_POWERLAW, NE_LOG_PARABOLA = 0, 1, 2
 NE_EXP_CUTOFF_POWERLAW, NE_EXP_CUTOFF_BROKEN_POWERLAW, NE_TABLE = 3, 4, 5
 INTEG_TRAPZ, INTEG_LOGLOG, INTEG_TRAPZ_PREFIX, INTEG_TRAPZ_FP32 = 0, 1, 2, 3
+INTEG_FOLD_PHI = 0x100  # flag: the phi grid is mirror-symmetric (include/agnpy_b200.h)
 EC_ISO_MONO, EC_PS_BEHIND_JET, EC_SS_DISK, EC_BLR, EC_DT = 0, 1, 2, 3, 4
 TAU_SS_DISK, TAU_BLR, TAU_DT = 0, 1, 2
 TAU_PS_BEHIND_BLOB, TAU_PS_BEHIND_BLOB_MU_S, TAU_BLR_MU_S, TAU_DT_MU_S = 3, 4, 5, 6

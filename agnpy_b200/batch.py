@@ -141,6 +141,8 @@ class SedBatch:
         self.gamma = dev(grids.as_grid(gamma, "gamma"))
         self.mu = dev(grids.mu_to_integrate if mu is None else grids.as_grid(mu, "mu"))
         self.phi = dev(grids.phi_to_integrate if phi is None else grids.as_grid(phi, "phi"))
+        if process in _EC:  # mirror-symmetric phi grid: the EC kernels may fold it
+            self.integ |= grids.phi_fold_flag(grids.phi_to_integrate if phi is None else phi)
         self.nu_seed = dev(grids.nu_to_integrate if nu_seed is None else nu_seed)
         self.l_unit = dev(np.logspace(-5, 5, int(l_size)) if process in _TAU_OFF_AXIS
                           else np.logspace(0, 5, int(l_size)))

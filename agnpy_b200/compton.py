@@ -5,7 +5,7 @@ import numpy as np
 
 from . import _core, _lib, spectra
 from .grids import (as_grid, gamma_e_to_integrate, integrator_code, mu_to_integrate,
-                    nu_to_integrate, phi_to_integrate)
+                    nu_to_integrate, phi_fold_flag, phi_to_integrate)
 from .synchrotron import _blob_models, _ne_setup
 from .units import strip, wrap
 
@@ -78,7 +78,7 @@ def _ec_call(variant, nu, z, d_L, delta_D, mu_s, R_b, tgt, n_e, args, integrator
     _core.model_row(models, 0, z=float(z), d_L=strip(d_L, "cm", "d_L"), delta_D=float(delta_D),
                     mu_s=float(mu_s), R_b=strip(R_b, "cm", "R_b"), ne=par, tgt=tgt)
     sed = _core.ec_sed_host(variant, models, kind, np.ravel(nu_hz), gamma, mu, n_mu, phi,
-                            ne_table, integrator_code(integrator))
+                            ne_table, integrator_code(integrator) | phi_fold_flag(phi))
     return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
 
 

@@ -13,11 +13,15 @@ namespace agb {
 constexpr size_t kChunkBytes = (size_t)1 << 30;  // scratch budget per batch chunk
 
 static bool bad_kind(int k) { return k < AGNPY_NE_POWERLAW || k > AGNPY_NE_TABLE; }
-static bool bad_integ(int i) { return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_FP32; }
+static bool bad_integ(int i) {
+    i &= ~AGNPY_INTEG_FOLD_PHI;
+    return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_FP32;
+}
 static const double* row_at(const double* table, int m0, int n_gamma) {
     return table ? table + (size_t)m0 * n_gamma : nullptr;  // tables are [n_models][n_gamma]
 }
 static int plain_integ(int i) {
+    i &= ~AGNPY_INTEG_FOLD_PHI;
     return (i == AGNPY_INTEG_TRAPZ_PREFIX || i == AGNPY_INTEG_TRAPZ_FP32) ? AGNPY_INTEG_TRAPZ : i;
 }
 

@@ -65,12 +65,25 @@ __device__ __forceinline__ double disk_epsilon(double L_disk, double M_BH, doubl
 //                        ang[m][2][j] = b_j = 1/(eps_j (1 - cos psi_j))
 //                        ang[m][3][j] = W_j        np.trapz weights x geometric factor
 //                        ang[m][4][j] = c_j = 2 eps_j (1 - cos psi_j)   (mask threshold on G)
+//                        ang[m][5][j], ang[m][6][j] = 1 - cos psi and W of the mirror partner
+//                                                     (folded phi axis, see below; W = 0: none)
+// Folding (AGNPY_INTEG_FOLD_PHI): when the phi grid is mirror-symmetric, phi_i + phi_{n-1-i} =
+// 2 pi m, cos phi -- hence cos psi, b and c -- takes the same value at both points of a mirror
+// pair, up to the last bit of cos().  The table then holds one entry per mirror pair with the
+// weight W_i + W_partner in column 3, so the main kernel evaluates every distinct integrand point
+// once (half the points of the default grid).  The partner's own 1 - cos psi and weight are kept
+// so that the one decision that is sensitive to the last bit -- on which side of a table entry
+// G_k the pair's threshold c falls -- is still taken for each partner separately with the
+// reference's formula whenever c is inside the guard band (ec_main_poly_kernel).
 // ---------------------------------------------------------------------------------------------
+constexpr int kAngCols = 7, kRawCols = 5;
 __device__ __forceinline__ void ec_pair_values(
     int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_mu,
-    const double* __restrict__ phi, int n_phi, int j, double& eps, double& omc, double& W) {
+    const double* __restrict__ phi, int n_phi, int imu, int iphi, double& eps, double& omc,
+    double& W) {
     const double* t = M.tgt;
     double cpsi;
+    const int j = iphi;  // ring torus: the pair index is the phi index
     if (variant == AGNPY_EC_PS_BEHIND_JET) {  // external_compton.py:226: mu = 1, phi = 0
         eps = t[0];
         cpsi = cos_psi(M.mu_s, 1.0, 0.0);
@@ -82,7 +95,6 @@ __device__ __forceinline__ void ec_pair_values(
         cpsi = cos_psi(M.mu_s, mu_dt, phi[j]);
         W = trapz_weight(phi, j, n_phi);
     } else {
-        int imu = j / n_phi, iphi = j - imu * n_phi;
         double wphi = trapz_weight(phi, iphi, n_phi);
         if (variant == AGNPY_EC_ISO_MONO) {  // :127-132
             eps = t[0];
@@ -117,15 +129,31 @@ __device__ __forceinline__ void ec_pair_values(
 }
 
 // unsorted pair values of one model: raw[m][0][j] = eps_j, [1][j] = 1 - cos psi_j, [2][j] = W_j
+// (folded: W_j + W_partner), [3][j], [4][j] = 1 - cos psi and W of the mirror partner.
+// n_phi_eff = n_phi (plain) or ceil(n_phi / 2) (folded): pair j = (imu, iphi < n_phi_eff).
 __device__ __forceinline__ void ec_pairs_role(
     int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_mu,
-    const double* __restrict__ phi, int n_phi, int n_pairs, double* __restrict__ raw, int j) {
+    const double* __restrict__ phi, int n_phi, int n_phi_eff, int n_pairs, double* __restrict__ raw,
+    int j) {
     if (j >= n_pairs) return;
-    double eps, omc, W;
-    ec_pair_values(variant, M, mu, n_mu, phi, n_phi, j, eps, omc, W);
+    int imu = 0, iphi = j;
+    if (variant != AGNPY_EC_PS_BEHIND_JET && variant != AGNPY_EC_DT) {
+        imu = j / n_phi_eff;
+        iphi = j - imu * n_phi_eff;
+    }
+    double eps, omc, W, omc_p = 0.0, W_p = 0.0;
+    ec_pair_values(variant, M, mu, n_mu, phi, n_phi, imu, iphi, eps, omc, W);
+    const int iphi_p = n_phi - 1 - iphi;
+    if (n_phi_eff != n_phi && iphi_p != iphi) {
+        double eps_p;
+        ec_pair_values(variant, M, mu, n_mu, phi, n_phi, imu, iphi_p, eps_p, omc_p, W_p);
+        W = W + W_p;
+    }
     raw[j] = eps;
     raw[n_pairs + j] = omc;
     raw[2 * n_pairs + j] = W;
+    raw[3 * n_pairs + j] = omc_p;
+    raw[4 * n_pairs + j] = W_p;
 }
 
 // One 1024-thread block takes one segment of kPairSeg consecutive pairs, one pair per thread,
@@ -171,6 +199,8 @@ __device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ ra
         row[2 * n_pairs + j] = 1.0 / (e * o);
         row[3 * n_pairs + j] = w;
         row[4 * n_pairs + j] = 2.0 * (e * o);
+        row[5 * n_pairs + j] = raw[3 * n_pairs + src];
+        row[6 * n_pairs + j] = raw[4 * n_pairs + src];
     }
 }
 
@@ -254,8 +284,10 @@ __global__ void __launch_bounds__(128) ec_tables_kernel(
                       integ, gt + (size_t)m * 5 * n_gamma,
                       hull + 2 * m, s_hull);
     } else if (bx < 1 + nB) {
-        ec_pairs_role(variant, M, mu, n_mu, phi, n_phi, n_pairs, raw + (size_t)m * 3 * n_pairs,
-                      (bx - 1) * 128 + threadIdx.x);
+        const int n_phi_eff =
+            (variant == AGNPY_EC_PS_BEHIND_JET || variant == AGNPY_EC_DT) ? n_phi : n_pairs / n_mu;
+        ec_pairs_role(variant, M, mu, n_mu, phi, n_phi, n_phi_eff, n_pairs,
+                      raw + (size_t)m * kRawCols * n_pairs, (bx - 1) * 128 + threadIdx.x);
     } else {
         bx -= 1 + nB;
         ec_nu_role(M, nu, gamma, n_gamma, nt + (size_t)m * n_nu * n_gamma, bx / nC,
@@ -328,7 +360,7 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
     const int klo = hull[2 * m], khi = hull[2 * m + 1];  // non-zero range of n_e
     __syncthreads();
 
-    const double* a_eps = ang + (size_t)m * 5 * n_pairs;
+    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
     const double* a_omc = a_eps + n_pairs;
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
@@ -535,7 +567,7 @@ __global__ void __launch_bounds__(kTab2Threads) ec_tables2_kernel(
     __shared__ unsigned long long s_x[kPairSeg];
     const int m = blockIdx.y;
     if ((int)blockIdx.x < n_seg) {
-        ec_pairs_sort_role(raw + (size_t)m * 3 * n_pairs, n_pairs, ang + (size_t)m * 5 * n_pairs,
+        ec_pairs_sort_role(raw + (size_t)m * kRawCols * n_pairs, n_pairs, ang + (size_t)m * kAngCols * n_pairs,
                            blockIdx.x, s_x);
     } else {
         ec_poly_row_role(models, nu, n_nu, gamma, n_gamma, gt, hull, rows,
@@ -627,11 +659,13 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
     }
     __syncthreads();
     const double* g_gm = gt + (size_t)m * 5 * n_gamma;
-    const double* a_eps = ang + (size_t)m * 5 * n_pairs;
+    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
     const double* a_omc = a_eps + n_pairs;
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
     const double* a_c = a_W + n_pairs;
+    const double* a_omc_p = a_c + n_pairs;  // mirror partner of a folded pair (W_p = 0: none)
+    const double* a_W_p = a_omc_p + n_pairs;
     const int klo = hull[2 * m], khi = hull[2 * m + 1];  // non-zero range of n_e
     const double* g_rows = rows + (size_t)m * n_nu * row_words;
     const int jbase = (slice * T + tid) * J;
@@ -711,14 +745,31 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
                     lo[jj] = n_gamma;
                 }
             }
+            double fold_corr = 0.0;  // see below; almost always 0
             if (doubt) {  // rare
                 tmin = INT_MAX;
                 tmax = 0;
 #pragma unroll
                 for (int jj = 0; jj < J; ++jj) {
-                    if (doubt & (1u << jj))
-                        lo[jj] = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc, jbase + jj, nu[i],
-                                                       models[m].z);
+                    if (doubt & (1u << jj)) {
+                        const int j = jbase + jj;
+                        lo[jj] = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc, j, nu[i], models[m].z);
+                        // folded pair: the mirror partner takes its own decision.  If it starts
+                        // at another index, the shared evaluation (weight W + W_p from lo) is off
+                        // by W_p times the integrand steps between the two indices.
+                        const double W_p = a_W_p[j];
+                        if (W_p != 0.0) {
+                            const int lo_p = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc_p, j, nu[i],
+                                                                   models[m].z);
+                            const int ka = max(min(lo[jj], lo_p), klo), kb = min(max(lo[jj], lo_p), khi + 1);
+                            double d = 0.0;
+                            for (int k = ka; k < kb; ++k) {
+                                const double2 qr = s_QR[k];
+                                d += (s_SP[k] - s_SP[k + 1]) + fma(qr.y, b[jj], qr.x * b2[jj]);
+                            }
+                            fold_corr += (lo_p < lo[jj]) ? W_p * d : -(W_p * d);
+                        }
+                    }
                     if (hc[jj] >= 0) { tmin = min(tmin, lo[jj]); tmax = max(tmax, lo[jj]); }
                 }
             }
@@ -769,6 +820,7 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
                 const int ks = max(lo[jj], klo);
                 if (ks <= khi) thread_sum = fma(a_W[jbase + jj], acc[jj] + s_SP[ks], thread_sum);
             }
+            thread_sum += fold_corr;
         }
         thread_sum = warp_sum(thread_sum);
         if ((tid & 31) == 0)
@@ -828,7 +880,7 @@ __global__ void __launch_bounds__(256) ec_main_fp32_kernel(
     const int klo = hull[2 * m], khi = hull[2 * m + 1];
     __syncthreads();
 
-    const double* a_eps = ang + (size_t)m * 5 * n_pairs;
+    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
     const double* a_omc = a_eps + n_pairs;
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
@@ -1024,7 +1076,7 @@ __global__ void __launch_bounds__(256) ec_prefix_kernel(
     const double* SP = s_S;
     const double* SQ = s_S + n1;
     const double* SR = s_S + 2 * n1;
-    const double* a_eps = ang + (size_t)m * 5 * n_pairs;
+    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
     const double* a_omc = a_eps + n_pairs;
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
@@ -1076,7 +1128,15 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
     p.J = 1;
     // measured on B200 (scripts/tune_ec.py): 128 threads x 8 pairs is the fastest tile at the
     // default 5000 pairs; smaller pair counts keep more, smaller tiles
-    if (integ == AGNPY_INTEG_TRAPZ) p.J = p.n_pairs >= 2048 ? 8 : p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
+    if (integ == AGNPY_INTEG_TRAPZ) {
+        p.J = p.n_pairs >= 2048 ? 8 : p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
+        // 8 pairs per thread run the gamma loop a little faster than 4, unless the last 1024-pair
+        // slice would be mostly padding (2500 folded pairs: 3 x 1024 wastes 19 %, 5 x 512 wastes 2 %)
+        if (p.J == 8) {
+            const int pad8 = (p.n_pairs + 1023) / 1024 * 1024, pad4 = (p.n_pairs + 511) / 512 * 512;
+            if (pad8 - pad4 > p.n_pairs / 12) p.J = 4;
+        }
+    }
     if (const char* e = getenv("AGNPY_B200_EC_PLAN")) {  // development knob: "T,J"
         int t = 0, j = 0;
         if (sscanf(e, "%d,%d", &t, &j) == 2 && t >= 32 && t <= 256 && t % 32 == 0 &&
@@ -1092,7 +1152,7 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
 // doubles of scratch per model
 static size_t ec_words(const EcPlan& p, int n_nu, int n_gamma) {
     return 5 * (size_t)n_gamma + 2      // gamma tables + hull (2 ints in one double slot, padded)
-           + 8 * (size_t)p.n_pairs      // pair table (sorted, 5 columns) + unsorted values (3)
+           + (kAngCols + kRawCols) * (size_t)p.n_pairs  // pair table (sorted) + unsorted values
            + 2 * (size_t)n_nu * n_gamma // {A,G}
            + (size_t)n_nu * ec_row_words(n_gamma)  // polynomial rows (np.trapz path)
            + (size_t)n_nu * p.S * p.W();
@@ -1122,10 +1182,19 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
            int n_nu, const double* gamma, int n_gamma, const double* mu, int n_mu,
            const double* phi, int n_phi, const double* ne_table, int integ, double* sed,
            double* ws, cudaStream_t stream) {
+    const bool fold_req = (integ & AGNPY_INTEG_FOLD_PHI) != 0 && getenv("AGNPY_B200_EC_NOFOLD") == nullptr;
+    integ &= ~AGNPY_INTEG_FOLD_PHI;
     const bool prefix = integ == AGNPY_INTEG_TRAPZ_PREFIX;
     const bool fp32 = integ == AGNPY_INTEG_TRAPZ_FP32;
     if (prefix || fp32) integ = AGNPY_INTEG_TRAPZ;  // same tables (trapz weights folded into wf)
     EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
+    // mirror-symmetric phi grid (the caller vouches for it): one table entry per mirror pair, if
+    // the folded (mu, phi) table still feeds the polynomial kernel
+    if (fold_req && integ == AGNPY_INTEG_TRAPZ && !fp32 && !prefix && n_phi >= 2 &&
+        (variant == AGNPY_EC_ISO_MONO || variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR)) {
+        EcPlan pf = ec_plan(variant, n_mu, (n_phi + 1) / 2, integ);
+        if (pf.n_pairs >= 512) p = pf;
+    }
     const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
     // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
     // source variants (<= n_phi pairs) stay on the v4 kernel
@@ -1136,8 +1205,8 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     double* rows = (double*)(nt + M * n_nu * n_gamma);  // 16-byte aligned: even word counts
     double* gt = rows + M * n_nu * ec_row_words(n_gamma);
     double* ang = gt + M * 5 * n_gamma;
-    double* raw = ang + M * 5 * p.n_pairs;
-    double* part = raw + M * 3 * p.n_pairs;
+    double* raw = ang + M * kAngCols * p.n_pairs;
+    double* part = raw + M * kRawCols * p.n_pairs;
     int* hull = (int*)(part + M * n_nu * p.S * p.W());
     {
         int nB = (p.n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;

@@ -52,6 +52,22 @@ def integrator_code(integrator):
         f"unsupported integrator {integrator!r}: use numpy.trapz or trapz_loglog")
 
 
+def phi_fold_flag(phi):
+    """INTEG_FOLD_PHI if the phi grid is mirror-symmetric -- phi[i] + phi[n-1-i] = 2 pi m for one
+    integer m, to 1e-13 -- else 0.  True for the reference's linspace(0, 2 pi, 50): cos phi, the
+    only way phi enters the Compton kernels (utils/geometry.py:5-12), then takes the same value at
+    both points of a mirror pair and the EC kernels evaluate each pair once."""
+    if phi is None:
+        return 0
+    p = np.asarray(phi, dtype=np.float64).ravel()
+    if p.size < 2 or not np.all(np.isfinite(p)):
+        return 0
+    s = p + p[::-1]
+    m = np.round(s[0] / (2 * np.pi))
+    tol = 1e-13 * max(1.0, float(np.max(np.abs(p))))
+    return _lib.INTEG_FOLD_PHI if np.all(np.abs(s - 2 * np.pi * m) <= tol) else 0
+
+
 def as_grid(x, name, ascending=True):
     if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 1 and x.flags.c_contiguous:
         a = x

@@ -269,6 +269,10 @@ def run_cuda(args):
     pts_per_launch = len(local) * N_NU * N_GAMMA * N_MU * N_PHI
     achieved = pts_per_launch * FLOPS_PER_POINT / (k_ms * 1e-3) / 1e12
     frac_pts = executed_point_fraction(local, g)
+    # mirror-symmetric phi grid: each mirror pair of (mu, phi) points is evaluated once
+    folded = bool(plan.integ & _lib.INTEG_FOLD_PHI) and not os.environ.get("AGNPY_B200_EC_NOFOLD")
+    if folded:
+        frac_pts *= ((N_PHI + 1) // 2) / N_PHI
     executed = pts_per_launch * frac_pts * EXEC_FLOPS_PER_POINT / (k_ms * 1e-3) / 1e12
     traffic = None
     tfile = ROOT / "profiles" / "ec_main_traffic.json"
@@ -396,12 +400,13 @@ def run_cuda(args):
             "algorithmic_flops_per_point": FLOPS_PER_POINT,
             "executed": {"tflops": executed, "frac": executed / (peak / 1e12),
                          "fp64_flops_per_visited_point": EXEC_FLOPS_PER_POINT,
-                         "visited_point_fraction": frac_pts},
+                         "visited_point_fraction": frac_pts, "phi_axis_folded": folded},
             "note": "frac > 1 is expected: the nominal 16 flop/point charges two divisions and the "
                     "(gamma,nu)/(mu,phi)-only subexpressions per point; the kernel hoists them "
                     "(2 DFMA per point: wf*K = P + Q b^2 + R b with per-(gamma,nu) tables) and "
-                    "skips points the reference masks to exactly 0. 'executed' counts only the "
-                    "DFMAs actually issued on visited points."},
+                    "skips points the reference masks to exactly 0; on a mirror-symmetric phi grid "
+                    "(the reference's default) the two points of a mirror pair share one "
+                    "evaluation. 'executed' counts only the DFMAs actually issued."},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} SED(s) of the same workload (oracle = reference numpy "
                                    "arithmetic, nu-chunked by 25), 1 thread",

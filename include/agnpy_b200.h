@@ -49,6 +49,12 @@ extern "C" {
 /* numpy.trapz with the integrand evaluated in FP32 (external Compton only; masks, angle sums and
  * prefactors stay FP64).  Opt-in reduced precision: rtol ~1e-6 instead of 1e-9. */
 #define AGNPY_INTEG_TRAPZ_FP32 3
+/* Flag, OR-ed into `integ` of agnpy_b200_ec_sed[_host] (ignored elsewhere): the caller vouches
+ * that the phi grid is mirror-symmetric, phi[i] + phi[n_phi-1-i] = 2 pi m for one integer m (true
+ * for the reference's linspace(0, 2 pi, 50)).  cos phi is then the same at both points of a mirror
+ * pair, and the (mu, phi) sum of the np.trapz path evaluates each pair once with the sum of the
+ * two weights.  Same integral, same grid; the mask decision is still taken per original point. */
+#define AGNPY_INTEG_FOLD_PHI 0x100
 
 /* external-Compton targets: agnpy/compton/external_compton.py */
 #define AGNPY_EC_ISO_MONO 0      /* :63-142   tgt = {epsilon_0, u_0}                              */

@@ -308,3 +308,61 @@ def test_ssc_batch_on_irregular_seed_grid():
         ref = orc.ssc_sed_flux(c["nu"], c["z"], c["d_L"], c["delta_D"] * (1 + i), c["B"], c["R_b"],
                                c["ne_kind"], c["ne_args"], gamma=c["gamma"], nu_seed=nu_seed)
         assert_parity(got[i], ref, what=f"irregular seed grid, model {i}")
+
+
+# ---- folded phi axis (AGNPY_INTEG_FOLD_PHI) -------------------------------------------------------
+def test_phi_fold_flag_host_logic_and_agreement(monkeypatch):
+    """mirror-symmetric phi grids are folded by default; the unfolded evaluation (knob) agrees to
+    rounding and both match the oracle; odd and even point counts, a grid symmetric about 0"""
+    from agnpy_b200 import grids
+    assert grids.phi_fold_flag(np.linspace(0, 2 * np.pi, 50)) == _lib.INTEG_FOLD_PHI
+    assert grids.phi_fold_flag(np.linspace(-np.pi, np.pi, 33)) == _lib.INTEG_FOLD_PHI
+    assert grids.phi_fold_flag(np.linspace(0.1, 2 * np.pi, 50)) == 0
+    assert grids.phi_fold_flag(np.sort(np.random.default_rng(0).uniform(0, 6, 30))) == 0
+    for n_phi, lo, hi in ((50, 0.0, 2 * np.pi), (51, 0.0, 2 * np.pi), (32, -np.pi, np.pi)):
+        c = cases.case_c2(n_nu=13, r=4e17, n_gamma=110, n_mu=40, n_phi=n_phi)
+        c = dict(c, phi=np.linspace(lo, hi, n_phi))
+        monkeypatch.delenv("AGNPY_B200_EC_NOFOLD", raising=False)
+        folded = blr_call(c)
+        monkeypatch.setenv("AGNPY_B200_EC_NOFOLD", "1")
+        plain = blr_call(c)
+        monkeypatch.delenv("AGNPY_B200_EC_NOFOLD", raising=False)
+        ref = cases.ORACLE_EC["blr"](c)
+        assert_parity(folded, ref, what=f"folded n_phi={n_phi}")
+        assert_parity(plain, ref, what=f"unfolded n_phi={n_phi}")
+        nz = ref != 0
+        assert np.max(np.abs(folded[nz] / plain[nz] - 1)) < 1e-12
+
+
+def test_phi_fold_keeps_the_mask_decision_of_each_mirror_partner():
+    """The one thing the last bit of cos(phi) can change is on which side of a table entry G_k a
+    pair's threshold c falls.  Build that case on purpose: one mirror partner is moved by 1e-7 rad
+    (its c by ~1e-9 relative) and a frequency is placed so that G_k(nu) lies between the two
+    thresholds -- the reference masks gamma_k for one partner and not for the other.  A folded
+    evaluation that let the representative decide for both would be off by ~1e-6 of the SED."""
+    from agnpy_b200 import _core, spectra
+    c = cases.case_c2(n_nu=3, r=3e17, n_gamma=120, n_mu=24, n_phi=48)   # 1152 pairs, 576 folded
+    phi = c["phi"].copy()
+    i_phi, i_mu, k = 9, 15, 70
+    phi[48 - 1 - i_phi] += 1e-7
+    mu_star = orc.mu_star_shell(c["mu"][i_mu], c["R_line"], c["r"])
+    cs = [2 * c["epsilon_line"] * (1 - orc.cos_psi(c["mu_s"], mu_star, p)) for p in (phi[i_phi], phi[48 - 1 - i_phi])]
+    assert 1e-10 < abs(cs[1] / cs[0] - 1) < 1e-7
+    G = np.sqrt(cs[0] * cs[1])                       # between the two thresholds
+    g = c["gamma"][k]
+    eps_s = G * g * g / (1 + G * g)                  # G = eps_s / (gamma (gamma - eps_s))
+    nu_star = eps_s * orc.MEC2 / orc.H_PLANCK / (1 + c["z"])
+    c = dict(c, phi=phi, nu=np.array([nu_star / 3, nu_star, nu_star * 3]))
+    # the reference really decides differently for the two partners at (nu_star, gamma_k)
+    gmin = [orc.gamma_min_compton(orc.nu_to_epsilon_prime(nu_star, c["z"]), c["epsilon_line"], c["mu_s"],
+                                  mu_star, p) for p in (phi[i_phi], phi[48 - 1 - i_phi])]
+    assert (g >= gmin[0]) != (g >= gmin[1])
+    ref = cases.ORACLE_EC["blr"](c)
+    kind, par = spectra.describe(ne_obj(c["ne_kind"], c["ne_args"]), q_args(c["ne_args"]))
+    models = _lib.make_models(1)
+    _core.model_row(models, 0, z=c["z"], d_L=c["d_L"], delta_D=c["delta_D"], mu_s=c["mu_s"], R_b=c["R_b"],
+                    ne=par, tgt=[c["L_disk"], c["xi_line"], c["epsilon_line"], c["R_line"], c["r"]])
+    for flag in (0, _lib.INTEG_FOLD_PHI):            # the caller vouches for the (almost) symmetric grid
+        got = _core.ec_sed_host(_lib.EC_BLR, models, kind, c["nu"], c["gamma"], c["mu"], c["mu"].size, phi,
+                                None, _lib.INTEG_TRAPZ | flag)[0]
+        assert_parity(got, ref, what=f"mirror partners straddling a table entry, flag={flag:#x}")
