@@ -93,6 +93,66 @@ __global__ void __launch_bounds__(128) tau_blr_path_kernel(
 
 // table[m][0][t] = p_t (target energy)   table[m][1][t] = (1 - cos psi)/2
 // table[m][2][t] = 1/(p_t (1-cos psi)/2)  table[m][3][t] = W_t
+// one (a, phi, l) entry of the on-axis variants (dt, blr, ss_disk): target energy p, 1 - cos psi
+// and the weight W = np.trapz weights x geometry, in the reference's operation order
+__device__ __forceinline__ void tau_onaxis_entry(
+    int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_a,
+    const double* __restrict__ phi, int n_phi, const double* __restrict__ l_unit, int n_l, int ia,
+    int iphi, int il, double& p, double& omc, double& W) {
+    const double* g = M.tgt;
+    const double wphi = trapz_weight(phi, iphi, n_phi);
+    if (variant == AGNPY_TAU_DT) {  // targets_absorption.py:520-530
+        double R_dt = g[3], r = g[4];
+        double l = l_unit[il] * r;
+        double llo = l_unit[il > 0 ? il - 1 : 0] * r, lhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r;
+        double wl = n_l < 2 ? 0.0 : (lhi - llo) * 0.5;
+        double x = sqrt(R_dt * R_dt + l * l);
+        double mu_l = l / x;
+        omc = 1.0 - cos_psi_t(M.mu_s, mu_l, phi[iphi]);
+        p = g[2];
+        W = wphi * wl * (omc / (x * x));
+    } else if (variant == AGNPY_TAU_BLR) {  // :333-349
+        double R_line = g[3], r = g[4];
+        double l = blr_l_at(l_unit, il, r, R_line);
+        double llo = blr_l_at(l_unit, il > 0 ? il - 1 : 0, r, R_line);
+        double lhi = blr_l_at(l_unit, il < n_l - 1 ? il + 1 : n_l - 1, r, R_line);
+        double wl = n_l < 2 ? 0.0 : (lhi - llo) * 0.5;
+        double mu_i = mu[ia];
+        double x = sqrt(R_line * R_line + l * l - 2.0 * l * R_line * mu_i);
+        double ratio = R_line / x;
+        double ms = sqrt(1.0 - ratio * ratio * (1.0 - mu_i * mu_i));
+        ms = ms * ((((l > mu_i * R_line) ? 1.0 : 0.0) - 0.5) * 2.0);
+        omc = 1.0 - cos_psi_t(M.mu_s, ms, phi[iphi]);
+        p = g[2];
+        W = trapz_weight(mu, ia, n_a) * wphi * wl * (omc / (x * x));
+    } else {  // AGNPY_TAU_SS_DISK :233-262
+        double M_BH = g[0], L_disk = g[1], eta = g[2];
+        double R_g = kG * M_BH / (kC * kC);
+        double r_t = g[5] / R_g, Rin_t = g[3] / R_g, Rout_t = g[4] / R_g;
+        double R = lin_at(Rin_t, Rout_t, n_a, ia);
+        double Rlo = lin_at(Rin_t, Rout_t, n_a, ia > 0 ? ia - 1 : 0);
+        double Rhi = lin_at(Rin_t, Rout_t, n_a, ia < n_a - 1 ? ia + 1 : n_a - 1);
+        double wR = n_a < 2 ? 0.0 : (Rhi - Rlo) * 0.5;
+        double l = l_unit[il] * r_t;
+        double llo = l_unit[il > 0 ? il - 1 : 0] * r_t, lhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r_t;
+        double wl = n_l < 2 ? 0.0 : (lhi - llo) * 0.5;
+        p = disk_eps(L_disk, M_BH, eta, R);
+        double phi_disk = 1.0 - sqrt(Rin_t / R);
+        double q = 1.0 + (R * R) / (l * l);
+        double mu_l = pow(q, -1.0 / 2.0);
+        omc = 1.0 - cos_psi_t(M.mu_s, mu_l, phi[iphi]);
+        W = wR * wphi * wl * (1.0 / (l * l) / (R * R) / pow(q, 3.0 / 2.0) * phi_disk / p * omc);
+    }
+}
+
+// phi[i] + phi[j] = 2 pi m for an integer m: cos phi takes the same value at both points
+__device__ __forceinline__ bool phi_mirror(const double* __restrict__ phi, int i, int j) {
+    const double s = phi[i] + phi[j];
+    const double m = rint(s / (2.0 * kPi));
+    const double tol = 1e-13 * fmax(1.0, fmax(fabs(phi[i]), fabs(phi[j])));
+    return fabs(s - 2.0 * kPi * m) <= tol;
+}
+
 __global__ void __launch_bounds__(128) tau_table_kernel(
     int variant, const agnpy_model_t* __restrict__ models, const double* __restrict__ mu, int n_a,
     const double* __restrict__ phi, int n_phi, const double* __restrict__ l_unit, int n_l,
@@ -150,53 +210,40 @@ __global__ void __launch_bounds__(128) tau_table_kernel(
         omc = 1.0 - cos_psi_t(mu_s, dz / x, atan2(dy, dx));
         p = g[2];
         W = trapz_weight(mu, ia, n_a) * wphi * wl * (omc / (x * x));
-    } else if (variant == AGNPY_TAU_DT) {  // targets_absorption.py:520-530
-        double R_dt = g[3], r = g[4];
-        double l = l_unit[il] * r;
-        double llo = l_unit[il > 0 ? il - 1 : 0] * r, lhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r;
-        double wl = n_l < 2 ? 0.0 : (lhi - llo) * 0.5;
-        double x = sqrt(R_dt * R_dt + l * l);
-        double mu_l = l / x;
-        omc = 1.0 - cos_psi_t(M.mu_s, mu_l, phi[iphi]);
-        p = g[2];
-        W = wphi * wl * (omc / (x * x));
-    } else if (variant == AGNPY_TAU_BLR) {  // :333-349
-        double R_line = g[3], r = g[4];
-        double l = blr_l_at(l_unit, il, r, R_line);
-        double llo = blr_l_at(l_unit, il > 0 ? il - 1 : 0, r, R_line);
-        double lhi = blr_l_at(l_unit, il < n_l - 1 ? il + 1 : n_l - 1, r, R_line);
-        double wl = n_l < 2 ? 0.0 : (lhi - llo) * 0.5;
-        double mu_i = mu[ia];
-        double x = sqrt(R_line * R_line + l * l - 2.0 * l * R_line * mu_i);
-        double ratio = R_line / x;
-        double ms = sqrt(1.0 - ratio * ratio * (1.0 - mu_i * mu_i));
-        ms = ms * ((((l > mu_i * R_line) ? 1.0 : 0.0) - 0.5) * 2.0);
-        omc = 1.0 - cos_psi_t(M.mu_s, ms, phi[iphi]);
-        p = g[2];
-        W = trapz_weight(mu, ia, n_a) * wphi * wl * (omc / (x * x));
-    } else {  // AGNPY_TAU_SS_DISK :233-262
-        double M_BH = g[0], L_disk = g[1], eta = g[2];
-        double R_g = kG * M_BH / (kC * kC);
-        double r_t = g[5] / R_g, Rin_t = g[3] / R_g, Rout_t = g[4] / R_g;
-        double R = lin_at(Rin_t, Rout_t, n_a, ia);
-        double Rlo = lin_at(Rin_t, Rout_t, n_a, ia > 0 ? ia - 1 : 0);
-        double Rhi = lin_at(Rin_t, Rout_t, n_a, ia < n_a - 1 ? ia + 1 : n_a - 1);
-        double wR = n_a < 2 ? 0.0 : (Rhi - Rlo) * 0.5;
-        double l = l_unit[il] * r_t;
-        double llo = l_unit[il > 0 ? il - 1 : 0] * r_t, lhi = l_unit[il < n_l - 1 ? il + 1 : n_l - 1] * r_t;
-        double wl = n_l < 2 ? 0.0 : (lhi - llo) * 0.5;
-        p = disk_eps(L_disk, M_BH, eta, R);
-        double phi_disk = 1.0 - sqrt(Rin_t / R);
-        double q = 1.0 + (R * R) / (l * l);
-        double mu_l = pow(q, -1.0 / 2.0);
-        omc = 1.0 - cos_psi_t(M.mu_s, mu_l, phi[iphi]);
-        W = wR * wphi * wl * (1.0 / (l * l) / (R * R) / pow(q, 3.0 / 2.0) * phi_disk / p * omc);
+    } else {
+        // on-axis variants (dt, blr, ss_disk): phi enters only through cos phi in cos psi
+        // (utils/geometry.py:5-12), so table entries that differ only by a mirror image of phi carry
+        // the same p and 1 - cos psi: they are merged into one entry with the sum of the weights
+        // and the other entry is retired (W = 0, p = 0: below threshold, skipped by the main
+        // kernel).  With mu_s = 1 exactly, sqrt(1 - mu_s^2) = 0 and cos psi does not depend on phi
+        // at all: one entry per (a, l) carries the whole phi integral.
+        tau_onaxis_entry(variant, M, mu, n_a, phi, n_phi, l_unit, n_l, ia, iphi, il, p, omc, W);
+        const int ip = n_phi - 1 - iphi;
+        bool dead = false;
+        if (M.mu_s == 1.0 && n_phi >= 2) {
+            if (iphi == 0) {
+                double wsum = 0.0;
+                for (int i = 0; i < n_phi; ++i) wsum += trapz_weight(phi, i, n_phi);
+                W = W / wphi * wsum;
+            } else {
+                dead = true;
+            }
+        } else if (ip != iphi && phi_mirror(phi, iphi, ip)) {
+            if (iphi < ip) {
+                double p2, omc2, W2;
+                tau_onaxis_entry(variant, M, mu, n_a, phi, n_phi, l_unit, n_l, ia, ip, il, p2, omc2, W2);
+                W = W + W2;
+            } else {
+                dead = true;
+            }
+        }
+        if (dead) { p = 0.0; W = 0.0; }
     }
     double* row = table + (size_t)m * 4 * n_t;
     double homc = omc / 2.0;
     row[t] = p;
     row[n_t + t] = homc;
-    row[2 * (size_t)n_t + t] = 1.0 / (p * homc);
+    row[2 * (size_t)n_t + t] = (p != 0.0) ? 1.0 / (p * homc) : 0.0;  // retired entry: keep it finite
     row[3 * (size_t)n_t + t] = W;
 }
 
@@ -241,6 +288,7 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
     const int t_end = min(n_t, (slice + 1) * kTauSlice);
     for (int t = slice * kTauSlice + threadIdx.x; t < t_end; t += blockDim.x) {
         double p = t_p[t], h = t_h[t], ic = t_ic[t], W = t_W[t];
+        if (__all_sync(__activemask(), W == 0.0)) continue;  // retired (folded phi axis) or weightless
 #pragma unroll
         for (int q = 0; q < kTauTN; ++q) {
             double s = e1[q] * p * h;  // == eps_1 * eps * (1 - cos psi) / 2, same rounding
