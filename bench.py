@@ -391,7 +391,7 @@ def run_cuda(args):
                                    "agnpy_b200_ec_sed_host)"},
         "integrand_gpts_per_s": total * N_NU * N_GAMMA * N_MU * N_PHI / (ms_per_step * 1e-3) / 1e9,
         "roofline": {
-            "bound": "fp64", "kernel": "ec_main_poly_kernel<J=8>", "achieved": achieved,
+            "bound": "fp64", "kernel": "ec_main_poly_kernel<J=4>", "achieved": achieved,
             "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
             "traffic": traffic,
             "peak_source": "live DFMA-chain microbenchmark agnpy_b200_fp64_peak on this GPU "
