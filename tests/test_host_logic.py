@@ -182,3 +182,32 @@ def test_fit_parameter_marshalling():
         fit.build_models(pars[:, :12], 1e28, "BrokenPowerLaw", "ec_blr_dt")
     ecbpl = fit.scale_spectral_parameters(np.array([[-8, 2, 3, 5.0, 4.0, 1.0, 7.0]]), "ExpCutoffBrokenPowerLaw")
     np.testing.assert_allclose(ecbpl[0], [1e-8, 2, 3, 1e5, 1e4, 10, 1e7])
+
+
+def test_phi_fold_flag():
+    """the host decides whether the EC kernels may fold the phi axis (AGNPY_INTEG_FOLD_PHI)"""
+    from agnpy_b200 import _lib, grids
+    F = _lib.INTEG_FOLD_PHI
+    assert grids.phi_fold_flag(grids.phi_to_integrate) == F          # the reference's default grid
+    assert grids.phi_fold_flag(np.linspace(0, 2 * np.pi, 51)) == F   # odd count: a self-mirrored point
+    assert grids.phi_fold_flag(np.linspace(-np.pi, np.pi, 20)) == F  # symmetric about 0 (m = 0)
+    assert grids.phi_fold_flag(np.linspace(0, np.pi, 20)) == 0       # sums to pi: cos is not mirrored
+    assert grids.phi_fold_flag(np.linspace(0.1, 2 * np.pi, 50)) == 0
+    p = np.linspace(0, 2 * np.pi, 50)
+    p[7] += 1e-9
+    assert grids.phi_fold_flag(p) == 0                               # one point off by 1e-9: no folding
+    assert grids.phi_fold_flag(None) == 0 and grids.phi_fold_flag(np.array([1.0])) == 0
+    assert grids.phi_fold_flag(np.array([0.0, np.nan, 2 * np.pi])) == 0
+    assert F & 0xff == 0                                             # a flag bit, not an integrator code
+
+
+def test_nu_indices_round_robin():
+    from agnpy_b200.batch import nu_indices
+    for n, world in ((9, 2), (8, 2), (1, 2), (1000, 8), (5, 8)):
+        seen = []
+        for r in range(world):
+            idx, per_rank = nu_indices(n, world, r)
+            assert per_rank == -(-n // world) and idx.size <= per_rank
+            assert np.all(np.diff(idx) == world) or idx.size <= 1    # ascending within a rank
+            seen.extend(idx.tolist())
+        assert sorted(seen) == list(range(n))
