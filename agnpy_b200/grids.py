@@ -1,4 +1,6 @@
 """Default integration grids and integrator selection (agnpy/utils/math.py:6-9, 55-119)."""
+import functools
+
 import numpy as np
 
 from . import _lib
@@ -56,16 +58,29 @@ def phi_fold_flag(phi):
     """INTEG_FOLD_PHI if the phi grid is mirror-symmetric -- phi[i] + phi[n-1-i] = 2 pi m for one
     integer m, to 1e-13 -- else 0.  True for the reference's linspace(0, 2 pi, 50): cos phi, the
     only way phi enters the Compton kernels (utils/geometry.py:5-12), then takes the same value at
-    both points of a mirror pair and the EC kernels evaluate each pair once."""
+    both points of a mirror pair and the EC kernels evaluate each pair once.
+    (Decided once per distinct grid: a fit loop passes the same array on every call.)"""
     if phi is None:
         return 0
-    p = np.asarray(phi, dtype=np.float64).ravel()
+    p = np.ascontiguousarray(phi, dtype=np.float64)
+    return _phi_fold_flag_of(p.tobytes())
+
+
+@functools.lru_cache(maxsize=64)
+def _phi_fold_flag_of(raw):
+    p = np.frombuffer(raw, dtype=np.float64)
     if p.size < 2 or not np.all(np.isfinite(p)):
         return 0
     s = p + p[::-1]
     m = np.round(s[0] / (2 * np.pi))
     tol = 1e-13 * max(1.0, float(np.max(np.abs(p))))
     return _lib.INTEG_FOLD_PHI if np.all(np.abs(s - 2 * np.pi * m) <= tol) else 0
+
+
+@functools.lru_cache(maxsize=64)
+def _ascending(raw):
+    a = np.frombuffer(raw, dtype=np.float64)
+    return bool((a[1:] > a[:-1]).all())
 
 
 def as_grid(x, name, ascending=True):
@@ -75,6 +90,6 @@ def as_grid(x, name, ascending=True):
         a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
     if a.size < 2:
         raise ValueError(f"{name}: need at least 2 grid points")
-    if ascending and not (a[1:] > a[:-1]).all():
+    if ascending and not _ascending(a.tobytes()):   # cached per distinct grid
         raise ValueError(f"{name}: grid must be strictly ascending")
     return a

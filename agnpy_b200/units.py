@@ -152,7 +152,10 @@ class Quantity:
         if isinstance(value, Quantity):
             unit = value.unit._combine(Unit(unit), 1) if unit else value.unit
             value = value.value
-        self.value = np.asarray(value, dtype=np.float64) if np.ndim(value) else float(value)
+        nd = getattr(value, "ndim", None)
+        if nd is None:
+            nd = np.ndim(value)
+        self.value = np.asarray(value, dtype=np.float64) if nd else float(value)
         self.unit = unit if isinstance(unit, Unit) else Unit(unit)
 
     # ---- the protocol the hot path uses ---------------------------------------------------
@@ -260,7 +263,10 @@ def strip(x, unit, name="argument"):
             v = x.to_value(unit)
         except Exception as exc:
             raise TypeError(f"{name}: cannot convert {getattr(x, 'unit', '?')} to '{unit}'") from exc
-        return np.asarray(v, dtype=np.float64) if np.ndim(v) else float(v)
+        nd = getattr(v, "ndim", None)  # np.ndim() is the slow way to ask an ndarray or a float
+        if nd is None:
+            nd = np.ndim(v)
+        return np.asarray(v, dtype=np.float64) if nd else float(v)
     if isinstance(x, (int, float, np.floating, np.integer)):
         return float(x)
     if isinstance(x, (np.ndarray, list, tuple)):
