@@ -156,9 +156,20 @@ __device__ __forceinline__ bool phi_mirror(const double* __restrict__ phi, int i
 __global__ void __launch_bounds__(128) tau_table_kernel(
     int variant, const agnpy_model_t* __restrict__ models, const double* __restrict__ mu, int n_a,
     const double* __restrict__ phi, int n_phi, const double* __restrict__ l_unit, int n_l,
-    int n_t, const double* __restrict__ path, double* __restrict__ table) {
+    int n_t, const double* __restrict__ path, double* __restrict__ table, int* __restrict__ n_live) {
     int m = blockIdx.y;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // is the whole phi grid mirror-symmetric?  (decided per block: every thread needs the answer
+    // to place its entry in the compacted table)
+    __shared__ int s_all_mirror;
+    if (threadIdx.x == 0) s_all_mirror = 1;
+    __syncthreads();
+    if (n_phi >= 2) {
+        for (int i = threadIdx.x; 2 * i < n_phi - 1; i += blockDim.x)
+            if (!phi_mirror(phi, i, n_phi - 1 - i)) s_all_mirror = 0;
+    }
+    __syncthreads();
+    const bool all_mirror = s_all_mirror != 0 && n_phi >= 2;
     if (t >= n_t) return;
     const agnpy_model_t& M = models[m];
     const double* g = M.tgt;
@@ -168,6 +179,8 @@ __global__ void __launch_bounds__(128) tau_table_kernel(
     double wphi = (variant == AGNPY_TAU_PS_BEHIND_BLOB || variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S)
                       ? 1.0 : trapz_weight(phi, iphi, n_phi);
     double p, omc, W;
+    int n_keep = n_phi;   // phi indices kept by the folding of the on-axis variants
+    bool dead = false;    // this entry is represented by its mirror image / by phi index 0
     if (variant == AGNPY_TAU_PS_BEHIND_BLOB) {  // targets_absorption.py:114-118 (closed form)
         p = g[0];
         omc = 1.0 - M.mu_s;
@@ -214,13 +227,12 @@ __global__ void __launch_bounds__(128) tau_table_kernel(
         // on-axis variants (dt, blr, ss_disk): phi enters only through cos phi in cos psi
         // (utils/geometry.py:5-12), so table entries that differ only by a mirror image of phi carry
         // the same p and 1 - cos psi: they are merged into one entry with the sum of the weights
-        // and the other entry is retired (W = 0, p = 0: below threshold, skipped by the main
-        // kernel).  With mu_s = 1 exactly, sqrt(1 - mu_s^2) = 0 and cos psi does not depend on phi
+        // and the mirror image is not stored.  With mu_s = 1 exactly, sqrt(1 - mu_s^2) = 0 and cos psi does not depend on phi
         // at all: one entry per (a, l) carries the whole phi integral.
         tau_onaxis_entry(variant, M, mu, n_a, phi, n_phi, l_unit, n_l, ia, iphi, il, p, omc, W);
         const int ip = n_phi - 1 - iphi;
-        bool dead = false;
         if (M.mu_s == 1.0 && n_phi >= 2) {
+            n_keep = 1;  // phi index 0 carries the whole phi integral
             if (iphi == 0) {
                 double wsum = 0.0;
                 for (int i = 0; i < n_phi; ++i) wsum += trapz_weight(phi, i, n_phi);
@@ -228,22 +240,30 @@ __global__ void __launch_bounds__(128) tau_table_kernel(
             } else {
                 dead = true;
             }
-        } else if (ip != iphi && phi_mirror(phi, iphi, ip)) {
-            if (iphi < ip) {
-                double p2, omc2, W2;
-                tau_onaxis_entry(variant, M, mu, n_a, phi, n_phi, l_unit, n_l, ia, ip, il, p2, omc2, W2);
-                W = W + W2;
+        } else if (all_mirror) {
+            n_keep = (n_phi + 1) / 2;  // phi indices 0 .. ceil(n/2)-1, each with its mirror image
+            if (iphi < n_keep) {
+                if (ip != iphi) {
+                    double p2, omc2, W2;
+                    tau_onaxis_entry(variant, M, mu, n_a, phi, n_phi, l_unit, n_l, ia, ip, il, p2, omc2, W2);
+                    W = W + W2;
+                }
             } else {
                 dead = true;
             }
         }
-        if (dead) { p = 0.0; W = 0.0; }
     }
+    // compacted table: only the kept phi indices are stored, t' = (ia * n_keep + iphi) * n_l + il,
+    // and the main kernel walks n_live[m] entries.  (Models of one call may differ: mu_s is theirs.)
+    const int live_total = (n_keep == n_phi) ? n_t : n_t / n_phi * n_keep;
+    if (t == 0) n_live[m] = live_total;
+    if (dead) return;
+    if (n_keep != n_phi) t = (ia * n_keep + iphi) * n_l + il;
     double* row = table + (size_t)m * 4 * n_t;
     double homc = omc / 2.0;
     row[t] = p;
     row[n_t + t] = homc;
-    row[2 * (size_t)n_t + t] = (p != 0.0) ? 1.0 / (p * homc) : 0.0;  // retired entry: keep it finite
+    row[2 * (size_t)n_t + t] = 1.0 / (p * homc);
     row[3 * (size_t)n_t + t] = W;
 }
 
@@ -266,7 +286,8 @@ constexpr int kTauSlice = 4096;  // table entries per block
 // grid = (n_slices, ceil(n_nu/TN), n_models); part[m][i][slice]
 __global__ void __launch_bounds__(256) tau_main_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
-    const double* __restrict__ table, int n_t, double* __restrict__ part, int blob_frame) {
+    const double* __restrict__ table, int n_t, const int* __restrict__ n_live,
+    double* __restrict__ part, int blob_frame) {
     __shared__ double red[32];
     const int slice = blockIdx.x, m = blockIdx.z, S = gridDim.x;
     const int i0 = blockIdx.y * kTauTN;
@@ -285,7 +306,13 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
         ie1[q] = 1.0 / e1[q];
         acc[q] = 0.0;
     }
-    const int t_end = min(n_t, (slice + 1) * kTauSlice);
+    const int live = n_live ? n_live[m] : n_t;  // live entries of this model (the stride stays n_t)
+    if (slice * kTauSlice >= live) {             // a slice behind the compacted table: nothing to add
+        if (threadIdx.x < kTauTN && i0 + threadIdx.x < n_nu)
+            part[((size_t)m * n_nu + i0 + threadIdx.x) * S + slice] = 0.0;
+        return;
+    }
+    const int t_end = min(live, (slice + 1) * kTauSlice);
     for (int t = slice * kTauSlice + threadIdx.x; t < t_end; t += blockDim.x) {
         // the weight first: a warp of retired (folded phi axis) or weightless entries costs one
         // 8-byte load per entry instead of four
@@ -405,7 +432,7 @@ int run_tau_synch(const agnpy_model_t* models, int n_models, int ne_kind, const 
     {
         dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
         timing_begin(stream);
-        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_s, part, 1);
+        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_s, nullptr, part, 1);
         timing_end(stream);
         note_launch();
     }
@@ -427,7 +454,7 @@ static int tau_n_t(int variant, int n_a, int n_phi, int n_l) {
 size_t tau_workspace_bytes(int variant, int n_models, int n_nu, int n_a, int n_phi, int n_l) {
     size_t n_t = tau_n_t(variant, n_a, n_phi, n_l);
     size_t S = (n_t + kTauSlice - 1) / kTauSlice;
-    return (4 * n_t + (size_t)n_nu * S + (size_t)n_l) * sizeof(double) * (size_t)n_models;
+    return (4 * n_t + (size_t)n_nu * S + (size_t)n_l + 1) * sizeof(double) * (size_t)n_models;
 }
 
 int run_tau(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
@@ -438,6 +465,7 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
     double* table = ws;
     double* part = table + (size_t)n_models * 4 * n_t;
     double* path = part + (size_t)n_models * n_nu * S;
+    int* n_live = reinterpret_cast<int*>(path + (size_t)n_models * n_l);  // live table entries per model
     int nl_eff = n_l, nphi_eff = n_phi;
     if (variant == AGNPY_TAU_PS_BEHIND_BLOB) { nl_eff = 1; nphi_eff = 1; }
     if (variant == AGNPY_TAU_PS_BEHIND_BLOB_MU_S) nphi_eff = 1;
@@ -448,13 +476,13 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
     {
         dim3 grid((n_t + 127) / 128, n_models);
         tau_table_kernel<<<grid, 128, 0, stream>>>(variant, models, mu, n_a, phi, nphi_eff, l_unit,
-                                                   nl_eff, n_t, path, table);
+                                                   nl_eff, n_t, path, table, n_live);
         note_launch();
     }
     {
         dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
         timing_begin(stream);
-        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, part, 0);
+        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, n_live, part, 0);
         timing_end(stream);
         note_launch();
     }
