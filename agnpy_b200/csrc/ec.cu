@@ -6,17 +6,24 @@
 //   agnpy/utils/geometry.py:5-55 (cos_psi, x_re_shell, mu_star_shell, x_re_ring)
 //   agnpy/targets/targets.py:289-323 (SSDisk statics)
 //
-// The reference broadcasts a full (gamma, mu, phi, nu) array (8 GB at the default grids).
-// Here a block owns one output frequency and a slice of (mu,phi) "pairs"; each thread keeps
-// J pairs in registers and walks the gamma axis once, reading three per-(gamma,nu) values
-// that the block tabulated in shared memory.  With
+// The reference broadcasts a full (gamma, mu, phi, nu) array (8 GB at the default grids).  Here
+// every thread keeps a few (mu,phi) "pairs" in registers and walks the gamma axis, reading
+// per-(gamma,nu) values tabulated once per (nu, model).  With
 //     y = 1 - eps_s/gamma,  A = y + 1/y,  G = eps_s/(gamma^2 y),  b = 1/(eps (1 - cos psi))
-// the kernel of kernels.py:61-65 is   K = y + 1/y - 2t + t^2 = A + t (t - 2),  t = G b,
-// i.e. 4 FP64 instructions per integrand point (DMUL, DADD, DFMA, DFMA-accumulate) and no
-// division: the two divisions of the nominal count are hoisted to the (gamma,nu) table and
-// to the per-pair table.  The kinematic mask gamma >= gamma_min(nu, pair) is evaluated with
-// the reference's own operation order (kernels.py:36-40) and turned into a start index of
-// the gamma loop by a binary search of the (ascending) gamma grid.
+// the kernel of kernels.py:61-65 is   K = y + 1/y - 2t + t^2 = A + t (t - 2),  t = G b:
+// no division per point (the two of the nominal count are hoisted into the tables), and the
+// kinematic mask gamma >= gamma_min(nu, pair) becomes a start index of the gamma loop (first k
+// with G_k <= c = 2 eps (1 - cos psi)), re-decided with the reference's own operation order
+// (kernels.py:36-40) whenever c lies within a guard band of a table entry.
+//
+// Map of this file:
+//   ec_tables_kernel / ec_tables2_kernel   gamma table, pair table (sorted by c, optionally with
+//                                          the phi axis folded), {A,G} table, polynomial rows
+//   ec_main_poly_kernel<J>                 np.trapz, >= 512 pairs: 2 DFMA per point (the default)
+//   ec_main_kernel<INTEG,J>                trapz_loglog, and np.trapz with few pairs (4 instr/pt)
+//   ec_main_fp32_kernel<J>, ec_prefix_kernel   opt-in variants (FP32 integrand, suffix sums)
+//   ec_finish_kernel                       fixed-order sum of the warp partials x prefactor
+//   run_ec                                 plan, scratch carving, launches
 #include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
