@@ -144,6 +144,8 @@ class SedBatch:
         if process in _EC:  # mirror-symmetric phi grid: the EC kernels may fold it
             self.integ |= grids.phi_fold_flag(grids.phi_to_integrate if phi is None else phi)
         self.nu_seed = dev(grids.nu_to_integrate if nu_seed is None else nu_seed)
+        # normalisation grid of the thermal disk SED (targets/targets.py:151, 393-415)
+        self.nu_bb_norm = dev(grids.nu_to_integrate_targets)
         self.l_unit = dev(np.logspace(-5, 5, int(l_size)) if process in _TAU_OFF_AXIS
                           else np.logspace(0, 5, int(l_size)))
         self._pinned_in = self._pinned_out = self._d_models = self._d_out = None
@@ -183,7 +185,7 @@ class SedBatch:
                                      d_out.data_ptr(), st)
         elif p in _BB:
             rc = L.agnpy_b200_bb_sed(_BB[p], n, d_models.data_ptr(), self.nu.data_ptr(), self.n_nu,
-                                     self.nu_seed.data_ptr(), self.nu_seed.numel(), 100,
+                                     self.nu_bb_norm.data_ptr(), self.nu_bb_norm.numel(), 100,
                                      d_out.data_ptr(), st)
         else:
             v = _TAU[p]

@@ -11,7 +11,7 @@
 namespace agb {
 
 constexpr double kKb = 1.380649e-16;
-constexpr double kSigmaSB = 5.6703744191844314e-5;
+constexpr double kSigmaSB = 5.670374419e-5;  // astropy CODATA 2018 literal (5.670374419e-8 SI)
 
 __device__ __forceinline__ double planck_nu(double nu, double T) {
     double log_boltz = kH * nu / (kKb * T);

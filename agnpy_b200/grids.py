@@ -7,6 +7,7 @@ from . import _lib
 
 gamma_e_to_integrate = np.logspace(1, 9, 200)   # utils/math.py:6
 nu_to_integrate = np.logspace(5, 30, 200)        # utils/math.py:7  [Hz]
+nu_to_integrate_targets = np.logspace(3, 21, 100)  # targets/targets.py:151  [Hz]
 mu_to_integrate = np.linspace(-1, 1, 100)        # utils/math.py:8
 phi_to_integrate = np.linspace(0, 2 * np.pi, 50) # utils/math.py:9
 

@@ -5,7 +5,7 @@ reference)."""
 import numpy as np
 
 from . import _core, _lib, constants as const
-from .grids import nu_to_integrate
+from .grids import nu_to_integrate_targets
 from .units import strip, u, wrap
 
 __all__ = ["CMB", "PointSourceBehindJet", "SSDisk", "SphericalShellBLR", "RingDustTorus",
@@ -79,7 +79,7 @@ class SSDisk:
         if L_disk is not None:
             tgt.append(strip(L_disk, "erg s-1", "L_disk"))
         _core.model_row(models, 0, z=float(z), d_L=strip(d_L, "cm", "d_L"), mu_s=float(mu_s), tgt=tgt)
-        sed = _core.bb_sed_host(variant, models, np.ravel(nu_hz), nu_to_integrate, 100)
+        sed = _core.bb_sed_host(variant, models, np.ravel(nu_hz), nu_to_integrate_targets, 100)
         return wrap(sed[0].reshape(np.shape(nu_hz)), "erg cm-2 s-1")
 
     @staticmethod

@@ -766,7 +766,11 @@ def chunked_over_nu(fn, nu, chunk, *args, **kwargs):
 # `astropy.modeling.physical_models.BlackBody.evaluate(nu, T, scale=1)`:
 #   B_nu = 2 h nu^3 / (c^2 expm1(h nu / (k_B T)))   [erg s-1 cm-2 Hz-1 sr-1]
 # --------------------------------------------------------------------------
-SIGMA_SB = 5.6703744191844314e-5
+# astropy.constants (CODATA 2018): sigma_sb = 5.670374419e-8 W m-2 K-4, the truncated literal, not
+# 2 pi^5 k^4/(15 h^3 c^2) = 5.6703744191844e-8 (3e-11 apart; visible in the Wien tails)
+SIGMA_SB = 5.670374419e-5
+# targets/targets.py:151: the module's own frequency grid for the normalisation integrals
+NU_TO_INTEGRATE_TARGETS = np.logspace(3, 21, 100)
 
 
 def planck_nu(nu, T):
@@ -797,8 +801,8 @@ def disk_multi_T_bb_sed(nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s=1):
 
 
 def disk_multi_T_bb_norm_sed(nu, z, L_disk, M_BH, m_dot, R_in, R_out, d_L, mu_s=1, nu_norm=None):
-    """targets.py:393-415"""
-    nu_norm = default_nu_seed() if nu_norm is None else nu_norm
+    """targets.py:393-415 (integrated over targets.py:151, not the utils/math.py grid)"""
+    nu_norm = NU_TO_INTEGRATE_TARGETS if nu_norm is None else nu_norm
     F_nu_norm = disk_multi_T_bb_sed(nu_norm, z, M_BH, m_dot, R_in, R_out, d_L, mu_s) / nu_norm
     A = 4 * np.pi * d_L**2
     L = 2 * (trapz(F_nu_norm, nu_norm) * A)
