@@ -4,11 +4,17 @@ from .absorption import Absorption
 from .compton import ExternalCompton, SynchrotronSelfCompton
 from .ebl import EBL
 from .grids import (gamma_e_to_integrate, mu_to_integrate, nu_to_integrate, phi_to_integrate,
-                    trapz_fp32, trapz_loglog, trapz_prefix)
+                    trapz_loglog, trapz_prefix)
+from .spectra import (BrokenPowerLaw, ExpCutoffBrokenPowerLaw, ExpCutoffPowerLaw,
+                      InterpolatedDistribution, LogParabola, PowerLaw)
 from .synchrotron import ProtonSynchrotron, Synchrotron
+from .targets import CMB, Blob, PointSourceBehindJet, RingDustTorus, SphericalShellBLR, SSDisk
 from .units import Quantity, u
 
 __all__ = ["Synchrotron", "ProtonSynchrotron", "SynchrotronSelfCompton", "ExternalCompton", "Absorption", "EBL",
-           "trapz_loglog", "trapz_prefix", "trapz_fp32", "gamma_e_to_integrate", "nu_to_integrate", "mu_to_integrate",
+           "Blob", "CMB", "PointSourceBehindJet", "SSDisk", "SphericalShellBLR", "RingDustTorus",
+           "PowerLaw", "BrokenPowerLaw", "LogParabola", "ExpCutoffPowerLaw", "ExpCutoffBrokenPowerLaw",
+           "InterpolatedDistribution",
+           "trapz_loglog", "trapz_prefix", "gamma_e_to_integrate", "nu_to_integrate", "mu_to_integrate",
            "phi_to_integrate", "Quantity", "u"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -139,3 +139,13 @@ def ebl_absorption_host(z, nu, energy_ref, z_ref, values, sed=None):
                                                energy_ref.size, hptr(z_ref), z_ref.size, hptr(values),
                                                mult, hptr(out)), "agnpy_b200_ebl_absorption_host")
     return out
+
+
+def trapz_loglog_host(rows, x, intervals=False):
+    """rows [n_rows][n_x] integrated along the last axis with the reference's trapz_loglog"""
+    rows, x = f64(rows), f64(x)
+    n_rows, n_x = rows.shape
+    out = np.empty((n_rows, n_x - 1) if intervals else (n_rows,))
+    check(lib().agnpy_b200_trapz_loglog_host(hptr(rows), hptr(x), n_rows, n_x, int(bool(intervals)),
+                                             hptr(out)), "agnpy_b200_trapz_loglog_host")
+    return out

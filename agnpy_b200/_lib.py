@@ -14,7 +14,7 @@ LIB_PATH = _PKG / "libagnpy_b200.so"
 # constants of include/agnpy_b200.h
 NE_POWERLAW, NE_BROKEN_POWERLAW, NE_LOG_PARABOLA = 0, 1, 2
 NE_EXP_CUTOFF_POWERLAW, NE_EXP_CUTOFF_BROKEN_POWERLAW, NE_TABLE = 3, 4, 5
-INTEG_TRAPZ, INTEG_LOGLOG, INTEG_TRAPZ_PREFIX, INTEG_TRAPZ_FP32 = 0, 1, 2, 3
+INTEG_TRAPZ, INTEG_LOGLOG, INTEG_TRAPZ_PREFIX = 0, 1, 2
 INTEG_FOLD_PHI = 0x100  # flag: the phi grid is mirror-symmetric (include/agnpy_b200.h)
 EC_ISO_MONO, EC_PS_BEHIND_JET, EC_SS_DISK, EC_BLR, EC_DT = 0, 1, 2, 3, 4
 TAU_SS_DISK, TAU_BLR, TAU_DT = 0, 1, 2
@@ -24,6 +24,7 @@ BB_DISK, BB_DISK_NORM, BB_DT, BB_DT_NORM = 0, 1, 2, 3
 EXPORTS = [
     "agnpy_b200_version", "agnpy_b200_last_error", "agnpy_b200_launch_count",
     "agnpy_b200_fp64_peak", "agnpy_b200_kernel_timing", "agnpy_b200_kernel_timing_read",
+    "agnpy_b200_strict_reference", "agnpy_b200_trapz_loglog", "agnpy_b200_trapz_loglog_host",
     "agnpy_b200_synch_sed", "agnpy_b200_synch_sed_host",
     "agnpy_b200_ssc_sed", "agnpy_b200_ssc_sed_host",
     "agnpy_b200_ec_sed", "agnpy_b200_ec_sed_host",
@@ -103,6 +104,10 @@ def lib():
     ebl = [ip, dp, dp, ip, dp, ip, dp, ip, dp, ip, dp]
     L.agnpy_b200_ebl_absorption.argtypes = ebl + [vp]
     L.agnpy_b200_ebl_absorption_host.argtypes = ebl
+    tl = [dp, dp, C.c_longlong, ip, ip, dp]
+    L.agnpy_b200_trapz_loglog.argtypes = tl + [vp]
+    L.agnpy_b200_trapz_loglog_host.argtypes = tl
+    L.agnpy_b200_strict_reference.argtypes = [C.c_int]
     L.agnpy_b200_kernel_timing.argtypes = [C.c_int]
     L.agnpy_b200_kernel_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     for name in EXPORTS[3:]:
@@ -115,6 +120,28 @@ def check(rc, what):
     if rc != 0:
         msg = lib().agnpy_b200_last_error().decode()
         raise AgnpyB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def strict_reference(enable=None):
+    """Literal-reference switch of include/agnpy_b200.h (SSA attenuation, sigma(s)): set it (True /
+    False) or just query (None); returns the previous setting.  Also usable as
+    `with strict_reference_mode(): ...`."""
+    return bool(lib().agnpy_b200_strict_reference(-1 if enable is None else int(bool(enable))))
+
+
+class strict_reference_mode:
+    """context manager: evaluate the reference's literal formulas inside the block"""
+
+    def __init__(self, enable=True):
+        self.enable = enable
+
+    def __enter__(self):
+        self.prev = strict_reference(self.enable)
+        return self
+
+    def __exit__(self, *exc):
+        strict_reference(self.prev)
+        return False
 
 
 def launch_count():

@@ -48,22 +48,54 @@ def local_slice(n_models, world_size, rank):
     return lo, hi, per_rank
 
 
-def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu"):
-    """Run `local_compute(models[lo:hi]) -> tensor [hi-lo, n_nu]` on this rank's shard and
-    all-gather the blocks.  Without an initialised process group this is a plain call."""
-    import torch
+GATHER_MODES = ("all", "rank0", "none")
+
+
+class GatherBuffers:
+    """device staging for the one collective of a sharded call, allocated once per shape and kept by the
+    plan (a fit loop calls with the same batch size thousands of times)"""
+
+    def __init__(self):
+        self._key, self.block, self.out = None, None, None
+
+    def get(self, rows, cols, world, device, need_out):
+        import torch
+        key = (rows, cols, world, str(device))
+        if key != self._key:
+            self._key = key
+            self.block = torch.zeros(rows, cols, dtype=torch.float64, device=device)
+            self.out = None
+        if need_out and self.out is None:
+            self.out = torch.empty(world * rows, cols, dtype=torch.float64, device=device)
+        return self.block, self.out
+
+
+def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu", gather="all",
+                     buffers=None):
+    """Run `local_compute(models[lo:hi]) -> tensor [hi-lo, n_nu]` on this rank's shard and join the
+    blocks with ONE collective.  Without an initialised process group this is a plain call.
+    gather = "all":   all-gather, every rank returns the full [n, n_nu] (default);
+             "rank0": the same collective, but only rank 0 returns the result (the others None) -- the
+                      caller on the other ranks skips the device->host copy;
+             "none":  no collective: every rank returns its own shard [hi-lo, n_nu]."""
     import torch.distributed as dist
+    if gather not in GATHER_MODES:
+        raise ValueError(f"gather must be one of {GATHER_MODES}")
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return local_compute(models)
     rank = dist.get_rank(group)
     n = len(models)
     lo, hi, per_rank = local_slice(n, world, rank)
-    block = torch.zeros(per_rank, n_nu, dtype=torch.float64, device=device)
+    if gather == "none":
+        return local_compute(models[lo:hi]) if hi > lo else None
+    buffers = GatherBuffers() if buffers is None else buffers
+    block, out = buffers.get(per_rank, n_nu, world, device, True)
     if hi > lo:
         block[: hi - lo] = local_compute(models[lo:hi])
-    out = torch.empty(world * per_rank, n_nu, dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(out, block, group=group)
+    dist.all_gather_into_tensor(out, block, group=group)    # rows >= n are padding, cut below
+    if gather == "rank0" and rank != 0:
+        return None
     return out[:n]
 
 
@@ -76,7 +108,7 @@ def nu_indices(n_nu, world_size, rank):
     return np.arange(rank, n_nu, world_size), per_rank
 
 
-def nu_sharded_evaluate(local_compute, nu, n_models, group=None, device="cpu"):
+def nu_sharded_evaluate(local_compute, nu, n_models, group=None, device="cpu", buffers=None):
     """Frequency sharding: `local_compute(nu[idx]) -> tensor [n_models, len(idx)]` on this rank's
     frequencies (idx = rank, rank + world, ...), then ONE all-gather; returns [n_models, n_nu] on
     every rank."""
@@ -88,10 +120,10 @@ def nu_sharded_evaluate(local_compute, nu, n_models, group=None, device="cpu"):
     rank = dist.get_rank(group)
     n = len(nu)
     idx, per_rank = nu_indices(n, world, rank)
-    block = torch.zeros(per_rank, n_models, dtype=torch.float64, device=device)  # [nu, model]
+    buffers = GatherBuffers() if buffers is None else buffers
+    block, out = buffers.get(per_rank, n_models, world, device, True)             # [nu, model]
     if idx.size:
         block[: idx.size] = local_compute(nu[idx]).transpose(0, 1)
-    out = torch.empty(world * per_rank, n_models, dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(out, block, group=group)
     # out[r * per_rank + j] is frequency j * world + r: undo the interleave
     out = out.view(world, per_rank, n_models).transpose(0, 1).reshape(world * per_rank, n_models)
@@ -149,6 +181,8 @@ class SedBatch:
         self.l_unit = dev(np.logspace(-5, 5, int(l_size)) if process in _TAU_OFF_AXIS
                           else np.logspace(0, 5, int(l_size)))
         self._pinned_in = self._pinned_out = self._d_models = self._d_out = None
+        self._gather = GatherBuffers()
+        self._h2d_done = None       # event after the last pinned->device copy of the model table
 
     # -- buffers sized for the largest batch seen so far
     def _buffers(self, n):
@@ -198,34 +232,62 @@ class SedBatch:
         return d_out
 
     def _local(self, models):
-        """host models -> device result for this rank's shard (H2D from pinned memory)"""
+        """host models -> device result for this rank's shard (H2D from pinned memory).
+        The returned tensor is the plan's own output buffer: valid until the next call on this plan."""
         n = len(models)
         pin_in, _, d_models, d_out = self._buffers(n)
+        if self._h2d_done is not None:
+            # the previous call's pinned->device copy may still be queued behind its kernels:
+            # never rewrite the staging block under it
+            self._h2d_done.synchronize()
         pin_in.numpy()[...] = np.ascontiguousarray(models).view(np.float64).reshape(n, -1)
         d_models.copy_(pin_in, non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = self.torch.cuda.Event()
+        self._h2d_done.record(self.torch.cuda.current_stream(self.device))
         return self.launch(d_models, d_out)
 
-    def evaluate_device(self, models):
-        """as __call__ but returns the (gathered) device tensor without the D2H copy"""
+    def evaluate_device(self, models, gather="all", clone=False):
+        """as __call__ but returns the (gathered) device tensor without the D2H copy.  The tensor is
+        a buffer of the plan, overwritten by the next call; pass clone=True to own the result."""
         if self.shard == "nu":
             def local(nu_part):  # the plan already holds this rank's slice
                 return self._local(models)[:, : len(nu_part)]
-            return nu_sharded_evaluate(local, self.nu_full, len(models), self.group, self.device)
-        return sharded_evaluate(self._local, models, self.n_nu, self.group, self.device)
+            out = nu_sharded_evaluate(local, self.nu_full, len(models), self.group, self.device,
+                                      self._gather)
+        else:
+            out = sharded_evaluate(self._local, models, self.n_nu, self.group, self.device, gather,
+                                   self._gather)
+        return out.clone() if (clone and out is not None) else out
 
-    def __call__(self, models):
+    def _to_host(self, out, copy):
+        """device [n, w] -> pinned host memory; returns a view of the plan's pinned block (valid until
+        the next call) or, with copy=True, an array the caller owns"""
+        torch = self.torch
+        n, w = out.shape
+        if (self._pinned_out is None or self._pinned_out.shape[0] < n
+                or self._pinned_out.shape[1] != w):
+            self._pinned_out = torch.empty(n, w, dtype=torch.float64).pin_memory()
+        host = self._pinned_out[:n]
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        host = host.numpy()
+        return host.copy() if copy else host
+
+    def __call__(self, models, gather="all", copy=True):
+        """models (host) -> numpy [n_models, n_nu].
+        gather: see `sharded_evaluate` ("rank0": ranks != 0 return None and copy nothing back;
+                "none": every rank gets only its own shard).
+        copy=False returns a view of the plan's pinned result block, valid until the next call on
+        this plan (saves one host memcpy of the whole result per call)."""
         if models.dtype != _lib.MODEL_DTYPE:
             raise TypeError("models must be a numpy array of agnpy_b200._lib.MODEL_DTYPE")
-        torch = self.torch
-        with torch.cuda.device(self.device):
-            out = self.evaluate_device(models)
-            n, w = out.shape
-            if self._pinned_out is None or self._pinned_out.shape[0] < n or self._pinned_out.shape[1] != w:
-                self._pinned_out = torch.empty(n, w, dtype=torch.float64).pin_memory()
-            host = self._pinned_out[:n]
-            host.copy_(out, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        return host.numpy().copy()
+        with self.torch.cuda.device(self.device):
+            out = self.evaluate_device(models, gather)
+            if out is None:
+                self.torch.cuda.current_stream(self.device).synchronize()
+                return None
+            return self._to_host(out, copy)
 
 
 class GraphedSum:

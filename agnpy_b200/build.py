@@ -7,7 +7,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libagnpy_b200.so"
-SOURCES = ["runtime.cu", "synch_ssc.cu", "ec.cu", "tau.cu", "bb.cu", "targets.cu", "capi.cu"]
+SOURCES = ["runtime.cu", "synch_ssc.cu", "ec.cu", "tau.cu", "bb.cu", "targets.cu", "integrate.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

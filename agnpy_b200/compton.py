@@ -4,7 +4,7 @@ running on the fused FP64 CUDA kernels K2 / K3."""
 import numpy as np
 
 from . import _core, _lib, spectra
-from .grids import (as_grid, gamma_e_to_integrate, integrator_code, mu_to_integrate,
+from .grids import (as_grid, gamma_e_to_integrate, integrator_code, mu_to_integrate, np_trapz,
                     nu_to_integrate, phi_fold_flag, phi_to_integrate)
 from .synchrotron import _blob_models, _ne_setup
 from .units import strip, wrap
@@ -15,14 +15,14 @@ __all__ = ["SynchrotronSelfCompton", "ExternalCompton"]
 class SynchrotronSelfCompton:
     """synchrotron_self_compton.py:19-193"""
 
-    def __init__(self, blob, ssa=False, integrator=np.trapezoid):
+    def __init__(self, blob, ssa=False, integrator=np_trapz):
         self.blob = blob
         self.ssa = ssa
         self.integrator = integrator
 
     @staticmethod
     def evaluate_sed_flux(nu, z, d_L, delta_D, B, R_b, n_e, *args, ssa=False,
-                          integrator=np.trapezoid, gamma=gamma_e_to_integrate):
+                          integrator=np_trapz, gamma=gamma_e_to_integrate):
         """nu F_nu [erg cm-2 s-1] of SSC, synchrotron_self_compton.py:73-158; the seed
         synchrotron spectrum is evaluated at utils/math.py:7 `nu_to_integrate`."""
         nu_hz = strip(nu, "Hz", "nu")
@@ -92,7 +92,7 @@ class ExternalCompton:
     """external_compton.py:25-640.  `target` is an agnpy target (or an object of
     agnpy_b200.targets) recognised by class name."""
 
-    def __init__(self, blob, target, r=None, integrator=np.trapezoid):
+    def __init__(self, blob, target, r=None, integrator=np_trapz):
         self.blob = blob
         self.target = target
         self.r = r
@@ -120,7 +120,7 @@ class ExternalCompton:
     # ---- static evaluators, same signatures as the reference ---------------------------------
     @staticmethod
     def evaluate_sed_flux_iso_mono(nu, z, d_L, delta_D, mu_s, R_b, epsilon_0, u_0, n_e, *args,
-                                   integrator=np.trapezoid, gamma=gamma_e_to_integrate,
+                                   integrator=np_trapz, gamma=gamma_e_to_integrate,
                                    mu=mu_to_integrate, phi=phi_to_integrate):
         """EC on a monochromatic isotropic field (e.g. CMB), external_compton.py:63-142"""
         mu, phi = as_grid(mu, "mu"), as_grid(phi, "phi")
@@ -130,7 +130,7 @@ class ExternalCompton:
 
     @staticmethod
     def evaluate_sed_flux_ps_behind_jet(nu, z, d_L, delta_D, mu_s, R_b, epsilon_0, L_0, r, n_e,
-                                        *args, integrator=np.trapezoid,
+                                        *args, integrator=np_trapz,
                                         gamma=gamma_e_to_integrate):
         """EC on a point source behind the jet, external_compton.py:163-240"""
         tgt = [float(epsilon_0), strip(L_0, "erg s-1", "L_0"), strip(r, "cm", "r")]
@@ -139,7 +139,7 @@ class ExternalCompton:
 
     @staticmethod
     def evaluate_sed_flux_ss_disk(nu, z, d_L, delta_D, mu_s, R_b, M_BH, L_disk, eta, R_in, R_out,
-                                  r, n_e, *args, integrator=np.trapezoid,
+                                  r, n_e, *args, integrator=np_trapz,
                                   gamma=gamma_e_to_integrate, mu_size=100, phi=phi_to_integrate):
         """EC on a Shakura-Sunyaev disk, external_compton.py:261-373"""
         tgt = [strip(M_BH, "g", "M_BH"), strip(L_disk, "erg s-1", "L_disk"), float(eta),
@@ -149,7 +149,7 @@ class ExternalCompton:
 
     @staticmethod
     def evaluate_sed_flux_blr(nu, z, d_L, delta_D, mu_s, R_b, L_disk, xi_line, epsilon_line,
-                              R_line, r, n_e, *args, integrator=np.trapezoid,
+                              R_line, r, n_e, *args, integrator=np_trapz,
                               gamma=gamma_e_to_integrate, mu=mu_to_integrate,
                               phi=phi_to_integrate):
         """EC on a spherical-shell BLR, external_compton.py:398-490"""
@@ -161,7 +161,7 @@ class ExternalCompton:
 
     @staticmethod
     def evaluate_sed_flux_dt(nu, z, d_L, delta_D, mu_s, R_b, L_disk, xi_dt, epsilon_dt, R_dt, r,
-                             n_e, *args, integrator=np.trapezoid, gamma=gamma_e_to_integrate,
+                             n_e, *args, integrator=np_trapz, gamma=gamma_e_to_integrate,
                              phi=phi_to_integrate):
         """EC on a ring dust torus, external_compton.py:514-600"""
         tgt = [strip(L_disk, "erg s-1", "L_disk"), float(xi_dt), float(epsilon_dt),

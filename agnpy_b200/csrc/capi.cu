@@ -15,14 +15,14 @@ constexpr size_t kChunkBytes = (size_t)1 << 30;  // scratch budget per batch chu
 static bool bad_kind(int k) { return k < AGNPY_NE_POWERLAW || k > AGNPY_NE_TABLE; }
 static bool bad_integ(int i) {
     i &= ~AGNPY_INTEG_FOLD_PHI;
-    return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_FP32;
+    return i < AGNPY_INTEG_TRAPZ || i > AGNPY_INTEG_TRAPZ_PREFIX;
 }
 static const double* row_at(const double* table, int m0, int n_gamma) {
     return table ? table + (size_t)m0 * n_gamma : nullptr;  // tables are [n_models][n_gamma]
 }
 static int plain_integ(int i) {
     i &= ~AGNPY_INTEG_FOLD_PHI;
-    return (i == AGNPY_INTEG_TRAPZ_PREFIX || i == AGNPY_INTEG_TRAPZ_FP32) ? AGNPY_INTEG_TRAPZ : i;
+    return i == AGNPY_INTEG_TRAPZ_PREFIX ? AGNPY_INTEG_TRAPZ : i;
 }
 
 static int chunk_models(size_t bytes_per_model, int n_models) {
@@ -302,6 +302,15 @@ int agnpy_b200_tau_synch(int n_models, const agnpy_model_t* models, int ne_kind,
 }
 
 // ------------------------------------------------------------------------------------------
+int agnpy_b200_trapz_loglog(const double* y, const double* x, long long n_rows, int n_x, int intervals,
+                            double* out, void* stream_) {
+    if (int rc = need_device()) return rc;
+    if (n_rows < 1 || n_x < 2 || !y || !x || !out)
+        return fail(AGNPY_ERR_ARG, "trapz_loglog: bad sizes or null pointer");
+    return run_trapz_loglog(y, x, n_rows, n_x, intervals, out, (cudaStream_t)stream_);
+}
+
+// ------------------------------------------------------------------------------------------
 int agnpy_b200_bb_sed(int variant, int n_models, const agnpy_model_t* models, const double* nu,
                       int n_nu, const double* nu_norm, int n_norm, int n_R, double* sed,
                       void* stream_) {
@@ -549,6 +558,23 @@ int agnpy_b200_tau_host(int variant, int n_models, const agnpy_model_t* models,
     if (int rc = agnpy_b200_tau(variant, n_models, io.dev<agnpy_model_t>(i_m), io.dev<double>(i_nu), n_nu,
                                 io.dev<double>(i_mu), n_a, io.dev<double>(i_ph), n_phi,
                                 io.dev<double>(i_l), n_l, io.dev<double>(o_tau), io.st))
+        return rc;
+    return io.download();
+}
+
+int agnpy_b200_trapz_loglog_host(const double* y, const double* x, long long n_rows, int n_x,
+                                 int intervals, double* out) {
+    if (int rc = need_device()) return rc;
+    if (n_rows < 1 || n_x < 2 || !y || !x || !out)
+        return fail(AGNPY_ERR_ARG, "trapz_loglog_host: bad sizes or null pointer");
+    size_t out_n = (size_t)n_rows * (intervals ? (size_t)(n_x - 1) : 1);
+    HostIO io;
+    int i_y = io.in(y, 8 * (size_t)n_rows * n_x), i_x = io.in(x, 8 * (size_t)n_x);
+    int o = io.out(out, 8 * out_n);
+    if (int rc = io.commit()) return rc;
+    if (int rc = io.upload()) return rc;
+    if (int rc = agnpy_b200_trapz_loglog(io.dev<double>(i_y), io.dev<double>(i_x), n_rows, n_x, intervals,
+                                         io.dev<double>(o), io.st))
         return rc;
     return io.download();
 }

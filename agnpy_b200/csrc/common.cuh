@@ -196,10 +196,11 @@ __device__ __forceinline__ double R_synch(double x) {
 
 // synchrotron.py:64-68 attenuation 3u/tau, u = 1/2 + e^-t/t - (1-e^-t)/t^2.  The reference
 // formula cancels catastrophically for small tau (abs. error ~ ulp/tau^2); it is evaluated
-// here through its series u = sum_{n>=1} (-1)^(n+1) t^n (n+1)/(n+2)! for tau < 0.5.
-__device__ __forceinline__ double ssa_attenuation(double tau) {
+// here through its series u = sum_{n>=1} (-1)^(n+1) t^n (n+1)/(n+2)! for tau < 0.5 -- unless the
+// strict-reference switch (agnpy_b200_strict_reference) asks for the literal formula.
+__device__ __forceinline__ double ssa_attenuation(double tau, bool strict = false) {
     if (tau < 1e-3) return 1.0;
-    if (tau < 0.5) {
+    if (tau < 0.5 && !strict) {
         double term = tau / 2.0;  // t^n/(n+1)!  for n=1
         double u = 0.0, sgn = 1.0;
         for (int n = 1; n <= 24; ++n) {
@@ -211,15 +212,18 @@ __device__ __forceinline__ double ssa_attenuation(double tau) {
         return 3.0 * u / tau;
     }
     double e = exp(-tau);
-    double u = 0.5 + e / tau - (1.0 - e) / (tau * tau);
+    double u = 0.5 + e / tau - (1.0 - e) / (tau * tau);  // np.power(tau, 2) == tau * tau
     return 3.0 * u / tau;
 }
+// bit 1 of the `ssa` / `blob_frame` kernel arguments carries the strict-reference switch
+constexpr int kStrictBit = 2;
 
 // launch bookkeeping shared by all translation units (defined in runtime.cu)
 void note_launch(int n = 1);
 void* workspace(size_t bytes, cudaStream_t stream);
 int fail(int code, const char* what);
 int check_last(const char* what);
+bool strict_reference();  // agnpy_b200_strict_reference(): literal reference formulas where we deviate
 // CUDA-event bracket around the dominant kernel of a call (no-ops unless enabled)
 void timing_begin(cudaStream_t stream);
 void timing_end(cudaStream_t stream);

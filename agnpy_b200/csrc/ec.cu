@@ -21,7 +21,7 @@
 //                                          the phi axis folded), {A,G} table, polynomial rows
 //   ec_main_poly_kernel<J>                 np.trapz, >= 512 pairs: 2 DFMA per point (the default)
 //   ec_main_kernel<INTEG,J>                trapz_loglog, and np.trapz with few pairs (4 instr/pt)
-//   ec_main_fp32_kernel<J>, ec_prefix_kernel   opt-in variants (FP32 integrand, suffix sums)
+//   ec_prefix_kernel                       opt-in: np.trapz through suffix sums over gamma
 //   ec_finish_kernel                       fixed-order sum of the warp partials x prefactor
 //   run_ec                                 plan, scratch carving, launches
 #include <limits.h>
@@ -835,140 +835,6 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Opt-in FP32 integrand (AGNPY_INTEG_TRAPZ_FP32): the same kernel with the point loop in single
-// precision -- K = fmaf(t, t-2, A), acc = fmaf(wf, K, acc) -- while everything that decides
-// *which* points contribute stays in FP64: the mask index search runs on the double G table with
-// the same guard band / exact fallback, the pair weights, the (mu,phi) sum and the prefactor
-// are double.  wf is scaled by its per-model maximum so it fits the float range.  Accuracy is
-// that of ~100 float FMAs per gamma integral (measured rtol ~1e-6, tests/test_gpu_prefix.py);
-// it is never selected implicitly.
-// ---------------------------------------------------------------------------------------------
-template <int J>
-__global__ void __launch_bounds__(256) ec_main_fp32_kernel(
-    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
-    const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma, int search_iters,
-    const double2* __restrict__ nt, const double* __restrict__ ang, int n_pairs, int S,
-    double* __restrict__ part) {
-    extern __shared__ double sh[];
-    __shared__ double red[32];
-    __shared__ double s_scale;
-    const int i = blockIdx.y, m = blockIdx.z;
-    const int T = blockDim.x, tid = threadIdx.x, W_per_block = T >> 5;
-    const double* g_gm = gt + (size_t)m * 5 * n_gamma;
-    const double* g_f = g_gm + n_gamma;
-    const double2* AG = nt + ((size_t)m * n_nu + i) * n_gamma;
-    double* s_G = sh;                        // double: mask search
-    double* s_A = s_G + n_gamma;             // double: guard band
-    float* s_ff = reinterpret_cast<float*>(s_A + n_gamma);
-    float* s_Af = s_ff + n_gamma;
-    float* s_Gf = s_Af + n_gamma;
-    double mx = 0.0;
-    for (int k = tid; k < n_gamma; k += T) mx = fmax(mx, fabs(g_f[k]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        double v = 0.0;
-        for (int w = 0; w < W_per_block; ++w) v = fmax(v, red[w]);
-        s_scale = (v > 0.0 && v < kFmax) ? v : 1.0;
-    }
-    __syncthreads();
-    const double scale = s_scale;
-    for (int k = tid; k < n_gamma; k += T) {
-        double2 ag = AG[k];
-        s_G[k] = ag.y;
-        s_A[k] = ag.x;
-        s_ff[k] = (float)(g_f[k] / scale);
-        s_Af[k] = (float)ag.x;
-        s_Gf[k] = (float)ag.y;
-    }
-    const int klo = hull[2 * m], khi = hull[2 * m + 1];
-    __syncthreads();
-
-    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
-    const double* a_omc = a_eps + n_pairs;
-    const double* a_b = a_omc + n_pairs;
-    const double* a_W = a_b + n_pairs;
-    const double* a_c = a_W + n_pairs;
-    for (int slice = blockIdx.x; slice < S; slice += gridDim.x) {
-        float bf[J], acc[J];
-        double W[J], c[J];
-        int lo[J], hi[J];
-#pragma unroll
-        for (int jj = 0; jj < J; ++jj) {
-            int j = slice * (T * J) + jj * T + tid;
-            bool valid = j < n_pairs;
-            bf[jj] = valid ? (float)a_b[j] : 0.f;
-            W[jj] = valid ? a_W[j] : 0.0;
-            c[jj] = valid ? a_c[j] : -1.0;
-            acc[jj] = 0.f;
-            lo[jj] = 0;
-            hi[jj] = n_gamma;
-        }
-        for (int it = 0; it < search_iters; ++it) {
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj) {
-                int mid = (lo[jj] + hi[jj]) >> 1;
-                bool open = lo[jj] < hi[jj];
-                bool le = s_G[min(mid, n_gamma - 1)] <= c[jj];
-                hi[jj] = (open && le) ? mid : hi[jj];
-                lo[jj] = (open && !le) ? mid + 1 : lo[jj];
-            }
-        }
-        int kmin = INT_MAX, kmax = 0;
-#pragma unroll
-        for (int jj = 0; jj < J; ++jj) {
-            int k = lo[jj];
-            const double cj = c[jj], band = 1e-6 * cj;
-            int ka = min(k, n_gamma - 1), kb = max(k - 1, 0);
-            double Ga = s_G[ka], Aa = s_A[ka], Gb = s_G[kb], Ab = s_A[kb];
-            bool doubt = (k < n_gamma && (fabs(Ga - cj) <= band || Aa > 1e8)) ||
-                         (k > 0 && (fabs(Gb - cj) <= band || (Ab > 1e8 && Gb < kFmax)));
-            doubt = (doubt || !(cj < kFmax)) && cj > 0.0;
-            if (doubt) {
-                int j = slice * (T * J) + jj * T + tid;
-                k = first_unmasked_exact(g_gm, n_gamma, a_eps[j], nu_to_eps(nu[i], models[m].z, 1.0),
-                                         a_omc[j]);
-            }
-            lo[jj] = k;
-            if (cj > 0.0) { kmin = min(kmin, k); kmax = max(kmax, k); }
-        }
-        double thread_sum = 0.0;
-        if (khi >= 0) {
-            kmin = __reduce_min_sync(0xffffffffu, kmin);
-            kmax = __reduce_max_sync(0xffffffffu, kmax);
-            int kbeg = max(kmin, klo);
-            int kmid = min(max(kmax, kbeg), khi + 1);
-            for (int k = kbeg; k < kmid; ++k) {
-                float wf = s_ff[k], A = s_Af[k], G = s_Gf[k];
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) {
-                    float t = G * bf[jj];
-                    float K = fmaf(t, t - 2.f, A);
-                    if (k >= lo[jj]) acc[jj] = fmaf(wf, K, acc[jj]);
-                }
-            }
-            for (int k = kmid; k <= khi; ++k) {
-                float wf = s_ff[k], A = s_Af[k], G = s_Gf[k];
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) {
-                    float t = G * bf[jj];
-                    float K = fmaf(t, t - 2.f, A);
-                    acc[jj] = fmaf(wf, K, acc[jj]);
-                }
-            }
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj)
-                if (c[jj] > 0.0) thread_sum = fma(W[jj], (double)acc[jj], thread_sum);
-        }
-        thread_sum = warp_sum(thread_sum);
-        if ((tid & 31) == 0)
-            part[(((size_t)m * n_nu + i) * S + slice) * W_per_block + (tid >> 5)] = thread_sum * scale;
-    }
-}
-
 // prefactor of each evaluate_sed_flux_* (external_compton.py:133-142, 229-240, 361-373, 476-490,
 // 590-600), in the reference's operation order
 __device__ __forceinline__ double ec_prefactor(int variant, const agnpy_model_t& M, double nu_i) {
@@ -1192,12 +1058,11 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     const bool fold_req = (integ & AGNPY_INTEG_FOLD_PHI) != 0 && getenv("AGNPY_B200_EC_NOFOLD") == nullptr;
     integ &= ~AGNPY_INTEG_FOLD_PHI;
     const bool prefix = integ == AGNPY_INTEG_TRAPZ_PREFIX;
-    const bool fp32 = integ == AGNPY_INTEG_TRAPZ_FP32;
-    if (prefix || fp32) integ = AGNPY_INTEG_TRAPZ;  // same tables (trapz weights folded into wf)
+    if (prefix) integ = AGNPY_INTEG_TRAPZ;  // same tables (trapz weights folded into wf)
     EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
     // mirror-symmetric phi grid (the caller vouches for it): one table entry per mirror pair, if
     // the folded (mu, phi) table still feeds the polynomial kernel
-    if (fold_req && integ == AGNPY_INTEG_TRAPZ && !fp32 && !prefix && n_phi >= 2 &&
+    if (fold_req && integ == AGNPY_INTEG_TRAPZ && !prefix && n_phi >= 2 &&
         (variant == AGNPY_EC_ISO_MONO || variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR)) {
         EcPlan pf = ec_plan(variant, n_mu, (n_phi + 1) / 2, integ);
         if (pf.n_pairs >= 512) p = pf;
@@ -1205,7 +1070,7 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
     // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
     // source variants (<= n_phi pairs) stay on the v4 kernel
-    const bool v5 = integ == AGNPY_INTEG_TRAPZ && !fp32 && !prefix && !use_v4 && p.n_pairs >= 512;
+    const bool v5 = integ == AGNPY_INTEG_TRAPZ && !prefix && !use_v4 && p.n_pairs >= 512;
     const size_t M = (size_t)n_models;
     // carve: {A,G} table first (16-byte aligned: ws comes from cudaMalloc), then the rest
     double2* nt = (double2*)ws;
@@ -1302,24 +1167,7 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     timing_begin(stream);
 #define EC_LAUNCH(I, JJ) launch_main<I, JJ>(grid, p.T, smem, stream, models, nu, n_nu, gt, hull, \
                                             n_gamma, iters, nt, ang, p.n_pairs, p.S, part)
-    if (fp32) {
-        size_t smem32 = (size_t)n_gamma * (2 * sizeof(double) + 3 * sizeof(float));
-#define EC_LAUNCH32(JJ)                                                                            \
-    do {                                                                                           \
-        if (smem32 > 48 * 1024)                                                                    \
-            cudaFuncSetAttribute(ec_main_fp32_kernel<JJ>,                                          \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);        \
-        ec_main_fp32_kernel<JJ><<<grid, p.T, smem32, stream>>>(models, nu, n_nu, gt, hull, n_gamma, \
-                                                               iters, nt, ang, p.n_pairs, p.S, part); \
-    } while (0)
-        if (p.J == 8) EC_LAUNCH32(8);
-        else if (p.J == 4) EC_LAUNCH32(4);
-        else if (p.J == 2) EC_LAUNCH32(2);
-        else EC_LAUNCH32(1);
-#undef EC_LAUNCH32
-    } else if (v5) {
-        // handled above
-    } else if (integ == AGNPY_INTEG_LOGLOG) EC_LAUNCH(AGNPY_INTEG_LOGLOG, 1);
+    if (integ == AGNPY_INTEG_LOGLOG) EC_LAUNCH(AGNPY_INTEG_LOGLOG, 1);
     else if (p.J == 8) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 8);
     else if (p.J == 4) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 4);
     else if (p.J == 2) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 2);

@@ -40,6 +40,9 @@ int run_tau_synch(const agnpy_model_t* models, int n_models, int ne_kind, const 
                   const double* gamma, int n_gamma, const double* ne_table, const double* ssa_table,
                   int n_s, double margin_low, int integ, double* tau, double* ws, cudaStream_t stream);
 
+int run_trapz_loglog(const double* y, const double* x, long long n_rows, int n_x, int intervals,
+                     double* out, cudaStream_t stream);
+
 int run_bb(int variant, const agnpy_model_t* models, int n_models, const double* nu, int n_nu,
            const double* nu_norm, int n_norm, int n_R, double* sed, cudaStream_t stream);
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ void synch_store(const agnpy_model_t& M, double eps, 
         double lc = kLambdaC / kC;
         double pk = -1.0 / (8.0 * kPi * kMe * (eps * eps)) * (lc * lc * lc);
         double tau = 2.0 * (pk * acc_ssa) * M.R_b;
-        sed = sed * ssa_attenuation(tau);
+        sed = sed * ssa_attenuation(tau, (ssa & kStrictBit) != 0);
         if (tau_out) tau_out[(size_t)m * n_nu + i] = tau;
     }
     if (out_mode == 0) {
@@ -241,6 +241,7 @@ int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, in
                  const double* tab, int n_gamma, int ssa, int integ, int out_mode, double* out,
                  double* tau_out, double* eps_out, cudaStream_t stream, int nu_stride, int proton) {
     dim3 grid(n_nu, n_models);
+    if (ssa) ssa = 1 | (strict_reference() ? kStrictBit : 0);
     if (integ == AGNPY_INTEG_TRAPZ) {
         // 4 frequencies per warp amortise the per-gamma cube root once the grid fills the GPU; a
         // small grid (single call) keeps one block per frequency: shortest dependent chain

@@ -267,7 +267,18 @@ __global__ void __launch_bounds__(128) tau_table_kernel(
     row[3 * (size_t)n_t + t] = W;
 }
 
-// sigma(s) / (3/16 sigma_T), targets_absorption.py:34-42, with 1-beta^2 = 1/s
+// sigma(s) / (3/16 sigma_T), targets_absorption.py:34-42 in the reference's literal form (strict
+// switch): beta = sqrt(1 - 1/s), (1 - beta^2) [(3 - beta^4) ln((1+beta)/(1-beta)) - 2 beta (2 - beta^2)]
+__device__ __forceinline__ double sigma_shape_strict(double s) {
+    double beta = sqrt(1.0 - 1.0 / s);
+    double b2 = beta * beta;
+    double t1 = (3.0 - b2 * b2) * clipped_log((1.0 + beta) / (1.0 - beta));
+    double t2 = -2.0 * beta * (2.0 - b2);
+    double v = (1.0 - b2) * (t1 + t2);
+    return (s < 1.0) ? 0.0 : v;
+}
+// default: the same function with 1-beta^2 = 1/s and ln((1+beta)/(1-beta)) = ln((1+beta)^2 s), which
+// do not lose the ~2e-16 s the reference's 1 - fl(beta)^2 loses
 __device__ __forceinline__ double sigma_shape(double s, double inv_s) {
     double b2 = 1.0 - inv_s;
     double beta = sqrt(b2);
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
         int i = min(i0 + q, n_nu - 1);
         // targets_absorption.py:331: no Doppler factor for the external fields; :647 the blob
         // frame for the synchrotron field
-        e1[q] = nu_to_eps(nu[i], M.z, blob_frame ? M.delta_D : 1.0);
+        e1[q] = nu_to_eps(nu[i], M.z, (blob_frame & 1) ? M.delta_D : 1.0);
         ie1[q] = 1.0 / e1[q];
         acc[q] = 0.0;
     }
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
             // below the pair-production threshold sigma is exactly 0 (targets_absorption.py:41):
             // skip the sqrt/log when no lane of the warp is above it (NaN s keeps the slow path)
             if (__all_sync(__activemask(), s < 1.0 && W == W && fabs(W) <= kFmax)) continue;
-            double v = sigma_shape(s, ic * ie1[q]);
+            double v = (blob_frame & kStrictBit) ? sigma_shape_strict(s) : sigma_shape(s, ic * ie1[q]);
             acc[q] = fma(W, v, acc[q]);
         }
     }
@@ -432,7 +443,8 @@ int run_tau_synch(const agnpy_model_t* models, int n_models, int ne_kind, const 
     {
         dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
         timing_begin(stream);
-        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_s, nullptr, part, 1);
+        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_s, nullptr, part,
+                                                   1 | (strict_reference() ? kStrictBit : 0));
         timing_end(stream);
         note_launch();
     }
@@ -482,7 +494,8 @@ int run_tau(int variant, const agnpy_model_t* models, int n_models, const double
     {
         dim3 grid(S, (n_nu + kTauTN - 1) / kTauTN, n_models);
         timing_begin(stream);
-        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, n_live, part, 0);
+        tau_main_kernel<<<grid, 256, 0, stream>>>(models, nu, n_nu, table, n_t, n_live, part,
+                                                   strict_reference() ? kStrictBit : 0);
         timing_end(stream);
         note_launch();
     }

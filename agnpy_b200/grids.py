@@ -12,6 +12,12 @@ mu_to_integrate = np.linspace(-1, 1, 100)        # utils/math.py:8
 phi_to_integrate = np.linspace(0, 2 * np.pi, 50) # utils/math.py:9
 
 
+# numpy.trapz was renamed numpy.trapezoid in numpy 2.0 and removed in 2.4; the reference (numpy >= 1.24,
+# < 2.3) spells it np.trapz.  Resolved once here so that the package imports on either.
+np_trapz = getattr(np, "trapezoid", None) or getattr(np, "trapz")
+_NUMPY_TRAPZ = tuple(f for f in (getattr(np, "trapezoid", None), getattr(np, "trapz", None)) if f is not None)
+
+
 def trapz_prefix(*args, **kwargs):
     """Selector for the opt-in suffix-sum evaluation of numpy.trapz over gamma in the external
     Compton kernels (AGNPY_INTEG_TRAPZ_PREFIX): same integral and masks, ~8x fewer operations."""
@@ -19,40 +25,65 @@ def trapz_prefix(*args, **kwargs):
         "agnpy_b200.trapz_prefix only selects the device integrator; it is not a host function")
 
 
-def trapz_fp32(*args, **kwargs):
-    """Selector for the opt-in FP32-integrand evaluation of numpy.trapz in the external Compton
-    kernels (AGNPY_INTEG_TRAPZ_FP32): masks and outer sums stay FP64, rtol ~1e-6."""
-    raise NotImplementedError(
-        "agnpy_b200.trapz_fp32 only selects the device integrator; it is not a host function")
+def trapz_loglog(y, x, axis=-1, intervals=False):
+    """Log-log trapezoidal rule of the reference, agnpy/utils/math.py:55-119: each interval is
+    integrated as the power law through its end points; intervals with a zero end point or a repeated
+    abscissa contribute 0.  Same signature as the reference's function (`intervals=True` returns the
+    per-interval integrals instead of their sum).  Quantities keep their units (y.unit * x.unit).
 
-
-def trapz_loglog(*args, **kwargs):
-    """Selector for the device-side log-log trapezoidal rule (utils/math.py:55-119).
-    Pass it as `integrator=`; the integration itself happens inside the CUDA kernels."""
-    raise NotImplementedError(
-        "agnpy_b200.trapz_loglog only selects the device integrator; it is not a host function")
-
-
-_TRAPZ_NAMES = {"trapz", "trapezoid"}
+    Two roles: passed as `integrator=` to any evaluate_* it selects the fused device-side rule
+    (AGNPY_INTEG_LOGLOG); called directly it integrates `y` along `axis` on the GPU through
+    agnpy_b200_trapz_loglog_host (there is no CPU fallback: it needs a CUDA device)."""
+    from . import _core
+    from .units import Quantity as _Q
+    y_unit = getattr(y, "unit", None)
+    x_unit = getattr(x, "unit", None)
+    yv = np.asarray(getattr(y, "value", y), dtype=np.float64)
+    xv = np.asarray(getattr(x, "value", x), dtype=np.float64)
+    if xv.ndim != 1:
+        raise ValueError("x must be one-dimensional (the reference slices it along `axis` too)")
+    if yv.shape[axis] != xv.size:
+        raise ValueError(f"y has {yv.shape[axis]} samples along axis {axis}, x has {xv.size}")
+    moved = np.ascontiguousarray(np.moveaxis(yv, axis, -1))
+    rows = moved.reshape(-1, xv.size)
+    out = _core.trapz_loglog_host(rows, xv, bool(intervals))
+    out = out.reshape(moved.shape[:-1] + ((xv.size - 1,) if intervals else ()))
+    if intervals:
+        out = np.moveaxis(out, -1, axis)
+    elif out.ndim == 0:
+        out = out[()]
+    if y_unit is not None or x_unit is not None:
+        unit = (y_unit if y_unit is not None else 1) * (x_unit if x_unit is not None else 1)
+        return out * unit
+    return out
 
 
 def integrator_code(integrator):
-    """`integrator=` keyword -> AGNPY_INTEG_*.  Accepts numpy.trapz / numpy.trapezoid, the
-    reference's or this package's `trapz_loglog`, or the strings "trapz" / "trapz_loglog".
-    Anything else raises: there is no host fallback that could run an arbitrary callable."""
-    if integrator is None:
+    """`integrator=` keyword -> AGNPY_INTEG_*.  Decided by identity: numpy.trapz / numpy.trapezoid, this
+    package's `trapz_loglog` / `trapz_prefix`, or the strings "trapz" / "trapz_loglog" /
+    "trapz_prefix".  The reference's own `agnpy.utils.math.trapz_loglog` function object is recognised
+    by module + name (it cannot be imported here to compare identities).  Anything else raises --
+    there is no host fallback that could run an arbitrary callable, and a user function that merely
+    happens to be called `trapz` must not silently select the device rule."""
+    if integrator is None or any(integrator is f for f in _NUMPY_TRAPZ):
         return _lib.INTEG_TRAPZ
-    name = integrator if isinstance(integrator, str) else getattr(integrator, "__name__", "")
-    if name in _TRAPZ_NAMES:
-        return _lib.INTEG_TRAPZ
-    if name == "trapz_loglog":
+    if integrator is trapz_loglog:
         return _lib.INTEG_LOGLOG
-    if name == "trapz_prefix":
+    if integrator is trapz_prefix:
         return _lib.INTEG_TRAPZ_PREFIX
-    if name == "trapz_fp32":
-        return _lib.INTEG_TRAPZ_FP32
+    if isinstance(integrator, str):
+        code = {"trapz": _lib.INTEG_TRAPZ, "trapezoid": _lib.INTEG_TRAPZ,
+                "trapz_loglog": _lib.INTEG_LOGLOG, "trapz_prefix": _lib.INTEG_TRAPZ_PREFIX}.get(integrator)
+        if code is not None:
+            return code
+    name = getattr(integrator, "__name__", "")
+    module = getattr(integrator, "__module__", "") or ""
+    if name == "trapz_loglog" and module == "agnpy.utils.math":
+        return _lib.INTEG_LOGLOG
+    if name in ("trapz", "trapezoid") and module.split(".")[0] == "numpy":
+        return _lib.INTEG_TRAPZ     # e.g. numpy.lib.function_base.trapz of an older numpy
     raise ValueError(
-        f"unsupported integrator {integrator!r}: use numpy.trapz or trapz_loglog")
+        f"unsupported integrator {integrator!r}: use numpy.trapz / numpy.trapezoid or trapz_loglog")
 
 
 def phi_fold_flag(phi):

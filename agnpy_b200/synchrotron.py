@@ -4,7 +4,7 @@ fused FP64 CUDA kernel K1."""
 import numpy as np
 
 from . import _core, _lib, spectra
-from .grids import as_grid, gamma_e_to_integrate, integrator_code
+from .grids import as_grid, gamma_e_to_integrate, integrator_code, np_trapz
 from .units import strip, wrap
 
 __all__ = ["Synchrotron", "ProtonSynchrotron"]
@@ -32,13 +32,13 @@ class Synchrotron:
     """synchrotron.py:71-277.  `blob` is any object exposing z, d_L, delta_D, B, R_b, n_e
     (with `.parameters`) and gamma_e, e.g. an agnpy Blob."""
 
-    def __init__(self, blob, ssa=False, integrator=np.trapezoid):
+    def __init__(self, blob, ssa=False, integrator=np_trapz):
         self.blob = blob
         self.ssa = ssa
         self.integrator = integrator
 
     @staticmethod
-    def evaluate_tau_ssa(nu, z, d_L, delta_D, B, R_b, n_e, *args, integrator=np.trapezoid,
+    def evaluate_tau_ssa(nu, z, d_L, delta_D, B, R_b, n_e, *args, integrator=np_trapz,
                          gamma=gamma_e_to_integrate):
         """SSA optical depth, synchrotron.py:101-129; returns a plain ndarray."""
         nu_hz = strip(nu, "Hz", "nu")
@@ -50,7 +50,7 @@ class Synchrotron:
 
     @staticmethod
     def evaluate_sed_flux(nu, z, d_L, delta_D, B, R_b, n_e, *args, ssa=False,
-                          integrator=np.trapezoid, gamma=gamma_e_to_integrate):
+                          integrator=np_trapz, gamma=gamma_e_to_integrate):
         """nu F_nu [erg cm-2 s-1] of synchrotron radiation, synchrotron.py:131-211."""
         nu_hz = strip(nu, "Hz", "nu")
         kind, par, gamma, ne_t, ssa_t = _ne_setup(n_e, args, gamma, ssa)
@@ -90,12 +90,12 @@ class ProtonSynchrotron:
     """synchrotron/proton_synchrotron.py:14-187: synchrotron radiation of the protons of a blob
     (`blob.n_p`, `blob.gamma_p`); the reference has no self-absorption for protons."""
 
-    def __init__(self, blob, integrator=np.trapezoid):
+    def __init__(self, blob, integrator=np_trapz):
         self.blob = blob
         self.integrator = integrator
 
     @staticmethod
-    def evaluate_sed_flux(nu, z, d_L, delta_D, B, R_b, n_p, *args, integrator=np.trapezoid,
+    def evaluate_sed_flux(nu, z, d_L, delta_D, B, R_b, n_p, *args, integrator=np_trapz,
                           gamma=gamma_e_to_integrate):
         """proton_synchrotron.py:69-151"""
         nu_hz = strip(nu, "Hz", "nu")

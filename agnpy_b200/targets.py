@@ -4,7 +4,7 @@ path reads is kept (energy densities, black-body SEDs, printing and plotting sta
 reference)."""
 import numpy as np
 
-from . import _core, _lib, constants as const
+from . import _core, _lib, constants as const, cosmology as _cosmology
 from .grids import nu_to_integrate_targets
 from .units import strip, u, wrap
 
@@ -14,6 +14,17 @@ __all__ = ["CMB", "PointSourceBehindJet", "SSDisk", "SphericalShellBLR", "RingDu
 # rest wavelengths [Angstrom] of a few broad lines (Finke 2016, table 5)
 lines_dictionary = {"Lyalpha": 1215.67, "Lybeta": 1025.72, "CIV": 1549.06, "MgII": 2797.92,
                     "Hbeta": 4861.33, "Halpha": 6562.80}
+
+
+def _d_L_of(z, d_L=None, cosmology=None):
+    """d_L as a Quantity in cm: the given one, else the reference's `Distance(z=z, cosmology=...)`
+    (emission_regions/blob.py:81, targets.py:424, 614) through agnpy_b200.cosmology (Planck18) or any
+    object with astropy's `luminosity_distance(z)`"""
+    if d_L is not None:
+        return d_L
+    if cosmology is None or isinstance(cosmology, _cosmology.FlatLambdaCDM):
+        return _cosmology.luminosity_distance(float(z), cosmology) * u.cm
+    return cosmology.luminosity_distance(z)
 
 
 def _u_call(variant, tgt, r, blob, n_mu=50):
@@ -92,8 +103,9 @@ class SSDisk:
         """same, normalised to an integral luminosity L_disk, targets.py:393-415"""
         return SSDisk._bb(_lib.BB_DISK_NORM, nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s, L_disk)
 
-    def sed_flux(self, nu, z, d_L, mu_s=1):
-        """targets.py:417-427; d_L must be given (the reference derives it from z)"""
+    def sed_flux(self, nu, z, mu_s=1, d_L=None):
+        """targets.py:417-427; d_L = Distance(z) (Planck18) unless given"""
+        d_L = _d_L_of(z, d_L)
         return self.evaluate_multi_T_bb_norm_sed(nu, z, self.L_disk, self.M_BH, self.m_dot, self.R_in,
                                                  self.R_out, d_L, mu_s)
 
@@ -111,6 +123,7 @@ class SphericalShellBLR:
         if line not in lines_dictionary:
             raise NameError(f"{line} not available in the line dictionary")
         self.L_disk, self.xi_line, self.line, self.R_line = L_disk, xi_line, line, R_line
+        self.lambda_line = lines_dictionary[line] * u.Unit("Angstrom")
         lam_cm = lines_dictionary[line] * 1e-8
         self.epsilon_line = const.h * const.c / lam_cm / const.mec2
 
@@ -156,8 +169,9 @@ class RingDustTorus:
         """same, normalised to the torus luminosity, targets.py:602-610"""
         return RingDustTorus._bb(_lib.BB_DT_NORM, nu, z, T_dt, R_dt, d_L, L_dt)
 
-    def sed_flux(self, nu, z, d_L):
-        """targets.py:612-618; d_L must be given (the reference derives it from z)"""
+    def sed_flux(self, nu, z, d_L=None):
+        """targets.py:612-618; d_L = Distance(z) (Planck18) unless given"""
+        d_L = _d_L_of(z, d_L)
         L_dt = self.xi_dt * strip(self.L_disk, "erg s-1", "L_disk") * u.Unit("erg s-1")
         return self.evaluate_bb_norm_sed(nu, z, L_dt, self.T_dt, self.R_dt, d_L)
 
@@ -169,16 +183,29 @@ class RingDustTorus:
 
 
 class Blob:
-    """emission_regions/blob.py:61-151; d_L must be given (the reference derives it from z
-    with astropy's cosmology)."""
+    """emission_regions/blob.py:22-151: same constructor as the reference (d_L from z through the
+    cosmology, Planck18 by default), plus an optional explicit `d_L` as the last keyword."""
 
-    def __init__(self, R_b, z, d_L, delta_D, Gamma, B, n_e, gamma_e_size=200, n_p=None,
-                 gamma_p_size=200):
-        if delta_D <= 0:
+    def __init__(self, R_b=1e16 * u.cm, z=0.069, delta_D=10, Gamma=10, B=1 * u.G, n_e=None, n_p=None,
+                 xi=1.0, gamma_e_size=200, gamma_p_size=200, cosmology=None, d_L=None):
+        if not isinstance(delta_D, (int, float, np.integer, np.floating)) or delta_D <= 0:
             raise ValueError("delta_D must be a positive number")
-        self.R_b, self.z, self.d_L, self.delta_D, self.Gamma, self.B = R_b, z, d_L, delta_D, Gamma, B
-        self.n_e, self.n_p = n_e, n_p
+        from .spectra import PowerLaw
+        self.R_b, self.z, self.delta_D, self.Gamma, self.B = R_b, z, delta_D, Gamma, B
+        self.d_L = _d_L_of(z, d_L, cosmology)
+        self.n_e = PowerLaw() if n_e is None else n_e
+        self.n_p, self.xi = n_p, xi
         self.gamma_e_size, self.gamma_p_size = gamma_e_size, gamma_p_size
+
+    @property
+    def V_b(self):
+        return wrap(4 / 3 * np.pi * np.power(strip(self.R_b, "cm", "R_b"), 3), "cm3")
+
+    @property
+    def t_var(self):
+        """blob.py:99-104, in days like the reference"""
+        t = ((1 + self.z) * strip(self.R_b, "cm", "R_b")) / (const.c * self.delta_D)
+        return wrap(t / 86400.0, "d")
 
     @property
     def gamma_p(self):

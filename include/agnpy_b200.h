@@ -46,9 +46,8 @@ extern "C" {
  * points treat it as AGNPY_INTEG_TRAPZ).  Same integral, grid and masks; the gamma sum is
  * re-associated (differences ~1e-15).  Opt-in: see DESIGN.md section 4. */
 #define AGNPY_INTEG_TRAPZ_PREFIX 2
-/* numpy.trapz with the integrand evaluated in FP32 (external Compton only; masks, angle sums and
- * prefactors stay FP64).  Opt-in reduced precision: rtol ~1e-6 instead of 1e-9. */
-#define AGNPY_INTEG_TRAPZ_FP32 3
+/* (value 3 was an opt-in FP32-integrand mode in 0.1: removed -- slower than the FP64 default and
+ * less accurate) */
 /* Flag, OR-ed into `integ` of agnpy_b200_ec_sed[_host] (ignored elsewhere): the caller vouches
  * that the phi grid is mirror-symmetric, phi[i] + phi[n_phi-1-i] = 2 pi m for one integer m (true
  * for the reference's linspace(0, 2 pi, 50)).  cos phi is then the same at both points of a mirror
@@ -108,6 +107,18 @@ long long agnpy_b200_launch_count(void);
  * on the launching stream; for the roofline line of bench.py.  Not thread safe. */
 int agnpy_b200_kernel_timing(int enable);
 int agnpy_b200_kernel_timing_read(double* total_ms, long long* n_launches);
+/* Strict-reference switch.  Two functions are evaluated, by default, in a better-conditioned form
+ * than the reference's literal formula:
+ *   - the SSA attenuation 3u/tau, u = 1/2 + e^-tau/tau - (1 - e^-tau)/tau^2
+ *     (agnpy/synchrotron/synchrotron.py:64-68): series for tau < 0.5 (the literal form loses
+ *     ~ulp/tau^2, up to 3e-7 relative just above its tau = 1e-3 switch);
+ *   - sigma(s) (agnpy/absorption/targets_absorption.py:34-42): 1 - beta^2 = 1/s and
+ *     ln((1+beta)/(1-beta)) = ln((1+beta)^2 s) (the literal 1 - fl(beta)^2 loses ~2e-16 s).
+ * enable = 1 evaluates the reference's literal formulas instead (bit-compatible conditioning, for
+ * "rtol 1e-9 against numpy" assertions), 0 restores the default, -1 only queries.  Returns the
+ * previous setting.  Process-wide; initial value from the environment variable
+ * AGNPY_B200_STRICT_REFERENCE. */
+int agnpy_b200_strict_reference(int enable);
 /* measured FP64 peak of the current device [FLOP/s]: a dependent-free DFMA-chain
  * microbenchmark run for `ms` milliseconds (roofline denominator) */
 int agnpy_b200_fp64_peak(double ms, double* flops_per_s, void* stream);
@@ -208,12 +219,25 @@ int agnpy_b200_tau_synch_host(int n_models, const agnpy_model_t* models, int ne_
                               const double* ne_table, const double* ssa_table, int n_s,
                               double delta_margin_low, int integ, double* tau);
 
+/* ---- log-log trapezoidal rule on user arrays --------------------------------------------------
+ * replaces trapz_loglog(y, x, axis)   agnpy/utils/math.py:55-119   (the reference exports and tests
+ * it as a function, utils/tests/test_utils.py:30-39; inside the evaluate_* entry points the rule is
+ * fused into the kernels and selected with AGNPY_INTEG_LOGLOG).
+ * y is [n_rows][n_x] with the integration axis last, x is [n_x].  intervals = 0: out[n_rows] = the
+ * integral of every row; intervals != 0: out[n_rows][n_x - 1] = the per-interval integrals (the
+ * reference's `intervals=True`). */
+int agnpy_b200_trapz_loglog(const double* y, const double* x, long long n_rows, int n_x,
+                            int intervals, double* out, void* stream);
+int agnpy_b200_trapz_loglog_host(const double* y, const double* x, long long n_rows, int n_x,
+                                 int intervals, double* out);
+
 /* ---- thermal black-body SEDs (fit-wrapper components) -----------------------------------------
  * replaces SSDisk.evaluate_multi_T_bb_sed / evaluate_multi_T_bb_norm_sed
  *          agnpy/targets/targets.py:350-415
  *      and RingDustTorus.evaluate_bb_sed / evaluate_bb_norm_sed   agnpy/targets/targets.py:593-610
  * nu_norm[n_norm]: frequencies of the normalisation integral of AGNPY_BB_DISK_NORM
- * (utils/math.py:7 `nu_to_integrate` in the reference); ignored otherwise (may be NULL). */
+ * (targets/targets.py:151 `nu_to_integrate` = logspace(3, 21, 100) Hz in the reference -- the
+ * module's own grid, not the one of utils/math.py); ignored otherwise (may be NULL). */
 int agnpy_b200_bb_sed(int variant, int n_models, const agnpy_model_t* models, const double* nu,
                       int n_nu, const double* nu_norm, int n_norm, int n_R, double* sed,
                       void* stream);

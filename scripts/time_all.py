@@ -69,7 +69,6 @@ for n in (1, 256):
     run("C1 ssc loglog", "ssc", n, 100 * 200 * 200 + 200 * 200, 38, nu=c1["nu"], gamma=c1["gamma"], integrator="trapz_loglog")
     run("C2 ec_blr 200nu", "ec_blr", n, 2e8, 16, nu=g2["nu"], gamma=g2["gamma"], mu=g2["mu"], phi=g2["phi"])
     run("C2 ec_blr trapz_prefix", "ec_blr", n, 2e8, 16, nu=g2["nu"], gamma=g2["gamma"], mu=g2["mu"], phi=g2["phi"], integrator="trapz_prefix")
-    run("C2 ec_blr trapz_fp32", "ec_blr", n, 2e8, 16, nu=g2["nu"], gamma=g2["gamma"], mu=g2["mu"], phi=g2["phi"], integrator="trapz_fp32")
     run("C2 ec_blr loglog", "ec_blr", min(n, 16), 2e8, 30, nu=g2["nu"], gamma=g2["gamma"], mu=g2["mu"], phi=g2["phi"], integrator="trapz_loglog")
     run("C3 ec_dt 200nu", "ec_dt", n, 200 * 200 * 50, 16, nu=g2["nu"], gamma=g2["gamma"], phi=g2["phi"])
     run("ec_ss_disk 200nu", "ec_ss_disk", min(n, 64), 2e8, 16, nu=g2["nu"], gamma=g2["gamma"], phi=g2["phi"])

@@ -155,3 +155,34 @@ ORACLE_EC = {
         c["eta"], c["R_in"], c["R_out"], c["r"], c["ne_kind"], c["ne_args"],
         integrator=integ, gamma=c["gamma"], mu_size=c["mu_size"], phi=c["phi"]),
 }
+
+
+# --------------------------------------------------------------------------
+# C5: fit parameter vectors in the sherpa wrapper's flat order (SURVEY.md 8(d); ranges inside the
+# fit bounds of agnpy/fit/core.py:92-113, 151-157)
+# --------------------------------------------------------------------------
+C5_NU = np.logspace(10, 28, 100)
+# column ranges of the 23-parameter "ec_blr_dt" vector that each sherpa scenario takes
+# (agnpy/fit/sherpa_wrapper.py:55, 83-98, 157-172, 233-251)
+C5_COLUMNS = {
+    "ssc": list(range(0, 10)),
+    "ec_blr": list(range(0, 20)),
+    "ec_dt": list(range(0, 17)) + [20, 21, 22],
+    "ec_blr_dt": list(range(0, 23)),
+}
+
+
+def c5_parameter_vectors(B, seed=20261019):
+    """[B, 23]: log10_k, p1, p2, log10_gamma_b, log10_gamma_min, log10_gamma_max, z, delta_D, log10_B,
+    t_var, mu_s, log10_r, log10_L_disk, M_BH, m_dot, R_in, R_out, xi_line, lambda_line, R_line, xi_dt,
+    T_dt, R_dt"""
+    rng = np.random.default_rng(seed)
+    pars = np.zeros((B, 23))
+    delta = rng.uniform(10, 40, B)
+    pars[:, 0], pars[:, 1], pars[:, 2] = rng.uniform(-9, -7, B), rng.uniform(1.5, 2.5, B), rng.uniform(3, 4, B)
+    pars[:, 3], pars[:, 4], pars[:, 5] = rng.uniform(3.5, 5, B), np.log10(20), np.log10(5e7)
+    pars[:, 6], pars[:, 7], pars[:, 8], pars[:, 9] = 1.0, delta, rng.uniform(-1.5, 0, B), 86400.0
+    pars[:, 10] = (1 - 1 / delta**2) / np.sqrt(1 - 1 / delta**2)
+    pars[:, 11], pars[:, 12] = rng.uniform(17, 19, B), np.log10(2e46)
+    pars[:, 13:] = [M_BH, 1e26, 6 * R_G, 200 * R_G, 0.024, 1215.67, 1e17, 0.1, 1e3, R_DT]
+    return pars

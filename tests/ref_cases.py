@@ -81,6 +81,36 @@ class RefSide:
         return {"trapz": np.trapz, "trapz_loglog": ref_math.trapz_loglog}[name]
 
 
+class ProductSide(RefSide):
+    """the SAME case code as the reference side, run on `agnpy_b200` (the drop-in): class names,
+    argument order, Quantities and keyword arguments are those of the reference calls"""
+    is_product = True
+
+    def __init__(self):
+        import agnpy_b200
+        self.agnpy, self.u, self.const = agnpy_b200, agnpy_b200.u, None
+
+    def integ(self, name):
+        from agnpy_b200 import grids
+        return {"trapz": grids.np_trapz, "trapz_loglog": self.agnpy.trapz_loglog}[name]
+
+    def to_R_g_units(self, r_cm, M_g):
+        from agnpy_b200 import constants as const
+        return r_cm / (const.G * M_g / const.c**2)
+
+    def fit_sherpa(self, scenario, pars, nu):
+        from agnpy_b200.fit import FitSedBatch
+        model = FitSedBatch(nu, "BrokenPowerLaw", scenario=scenario)
+        return model.sherpa(nu * orc.H_PLANCK / EV_ERG, pars).T
+
+    def fit_gammapy(self, targets, pars, energy_eV):
+        from agnpy_b200.fit import FitSedBatch, scenario_of
+        model = FitSedBatch(energy_eV * EV_ERG / orc.H_PLANCK, "BrokenPowerLaw",
+                            scenario=scenario_of(targets))
+        kwargs = {n: pars[:, i] for i, n in enumerate(GAMMAPY_NAMES)}
+        return model.gammapy(energy_eV, norm=1.0, **kwargs).T
+
+
 def _val(x):
     """plain ndarray of a reference result (SEDs are Quantities in erg cm-2 s-1, taus plain)"""
     return np.asarray(getattr(x, "value", x), dtype=float)
@@ -444,7 +474,9 @@ def _scalars(side, A, idx):
     t = _targets(A)
     return np.array([float(t["disk"].R_g.to_value("cm")), float(t["blr"].epsilon_line),
                      float(t["dt"].epsilon_dt), float(t["dt"].R_dt.to_value("cm")),
-                     float(__import__("importlib").import_module("agnpy.utils.conversion").to_R_g_units(A.Q(1e17, "cm"), A.Q(cases.M_BH, "g")))])
+                     float(A.to_R_g_units(1e17, cases.M_BH) if getattr(A, "is_product", False) else
+                           __import__("importlib").import_module("agnpy.utils.conversion").to_R_g_units(
+                               A.Q(1e17, "cm"), A.Q(cases.M_BH, "g")))])
 
 
 @case("ebl_finke_2010", rtol=1e-12)
@@ -455,4 +487,105 @@ def _ebl(side, A, idx):
     if side == "orc":
         tab = orc.read_ebl_fits(cases.GOLDEN / "reference_data" / "ebl_models" / "frd_abs.fits.gz")
         return np.nan_to_num(orc.ebl_absorption(nu, z, *tab), nan=-1.0)
-    return np.nan_to_num(np.asarray(A.agnpy.EBL("finke_2010").absorption(A.Q(nu, "Hz"), z)), nan=-1.0)
+    kw = {"data_dir": cases.GOLDEN / "reference_data" / "ebl_models"} if getattr(A, "is_product", False) else {}
+    return np.nan_to_num(np.asarray(A.agnpy.EBL("finke_2010", **kw).absorption(A.Q(nu, "Hz"), z)), nan=-1.0)
+
+
+# ------------------------------------------------------------------------------------------
+# fit-wrapper level: the reference's own scenario functions
+# agnpy/fit/sherpa_wrapper.py:51-325 and gammapy_wrapper.py:161-181, 284-357, imported through
+# import-level stand-ins for sherpa / gammapy (oracle/astropy_stub/{sherpa,gammapy}); outputs [n_nu, n_vec]
+# ------------------------------------------------------------------------------------------
+N_FIT_VECTORS = 6
+EV_ERG = 1.602176634e-12
+
+
+def fit_oracle(scenario, row, nu, d_L, ssa=False):
+    """the wrapper's arithmetic on the oracle: parameter unpacking + log10 scaling
+    (sherpa_wrapper.py:29-48), R_b = c t_var delta_D / (1+z) (:64), component sum (:66-75, 122-150,
+    196-225, 276-325)"""
+    cols = cases.C5_COLUMNS[scenario]
+    p = dict(zip([("log10_k", "p1", "p2", "log10_gamma_b", "log10_gamma_min", "log10_gamma_max", "z",
+                   "delta_D", "log10_B", "t_var", "mu_s", "log10_r", "log10_L_disk", "M_BH", "m_dot",
+                   "R_in", "R_out", "xi_line", "lambda_line", "R_line", "xi_dt", "T_dt", "R_dt")[c]
+                  for c in cols], row))
+    ne = (10 ** p["log10_k"], p["p1"], p["p2"], 10 ** p["log10_gamma_b"], 10 ** p["log10_gamma_min"],
+          10 ** p["log10_gamma_max"])
+    z, delta_D, B = p["z"], p["delta_D"], 10 ** p["log10_B"]
+    R_b = (orc.C_LIGHT * p["t_var"] * delta_D) / (1 + z)
+    a = (nu, z, d_L, delta_D, B, R_b, "BrokenPowerLaw", ne)
+    sed = orc.synch_sed_flux(*a, ssa=ssa) + orc.ssc_sed_flux(*a, ssa=ssa)
+    if scenario == "ssc":
+        return sed
+    r, L_disk = 10 ** p["log10_r"], 10 ** p["log10_L_disk"]
+    gamma_ec = np.logspace(1, 9, 300)
+    sed = sed + orc.disk_multi_T_bb_norm_sed(nu, z, L_disk, p["M_BH"], p["m_dot"], p["R_in"],
+                                             p["R_out"], d_L)
+    if "dt" in scenario:
+        eps_dt = 2.7 * (orc.K_B * p["T_dt"] / orc.MEC2)
+        sed = sed + orc.dt_bb_norm_sed(nu, z, p["xi_dt"] * L_disk, p["T_dt"], p["R_dt"], d_L)
+        sed = sed + orc.ec_dt_sed_flux(nu, z, d_L, delta_D, p["mu_s"], R_b, L_disk, p["xi_dt"], eps_dt,
+                                       p["R_dt"], r, "BrokenPowerLaw", ne, gamma=gamma_ec)
+    if "blr" in scenario:
+        eps_line = orc.H_PLANCK * orc.C_LIGHT / (p["lambda_line"] * 1e-8) / orc.MEC2
+        sed = sed + orc.chunked_over_nu(
+            lambda nn: orc.ec_blr_sed_flux(nn, z, d_L, delta_D, p["mu_s"], R_b, L_disk, p["xi_line"],
+                                           eps_line, p["R_line"], r, "BrokenPowerLaw", ne,
+                                           gamma=gamma_ec), nu, 5)
+    return sed
+
+
+def _fit_sherpa(side, A, idx, scenario, store=None):
+    pars = cases.c5_parameter_vectors(N_FIT_VECTORS)[:, cases.C5_COLUMNS[scenario]]
+    nu = cases.C5_NU if idx is None else cases.C5_NU[idx]
+    key = f"fit_sherpa_{scenario}__d_L"
+    if side == "orc":
+        d_L = store[key]
+        return np.stack([fit_oracle(scenario, pars[i], nu, float(d_L[i]))
+                         for i in range(N_FIT_VECTORS)], axis=1)
+    import importlib
+    if getattr(A, "is_product", False):
+        return A.fit_sherpa(scenario, pars, nu)
+    sw = importlib.import_module("agnpy.fit.sherpa_wrapper")
+    fn = getattr(sw, f"_evaluate_sed_{scenario}_scenario")
+    n_e = A.agnpy.BrokenPowerLaw()
+    x = nu * orc.H_PLANCK / EV_ERG        # sherpa hands energies in eV
+    store[key] = np.array([float(importlib.import_module(
+        "astropy.coordinates").Distance(z=row[6]).to("cm").value) for row in pars])
+    return np.stack([_val(fn(x.copy(), [float(v) for v in row], n_e, False)) for row in pars], axis=1)
+
+
+for _sc in ("ssc", "ec_blr", "ec_dt", "ec_blr_dt"):
+    case(f"fit_sherpa_{_sc}", sub=(4 if _sc == "ssc" else 12), rtol=RTOL_EXP_TAIL)(
+        lambda side, A, idx, store=None, sc=_sc: _fit_sherpa(side, A, idx, sc, store))
+
+GAMMAPY_NAMES = ("log10_k", "p1", "p2", "log10_gamma_b", "log10_gamma_min", "log10_gamma_max", "z",
+                 "delta_D", "log10_B", "t_var", "mu_s", "log10_r", "log10_L_disk", "M_BH", "m_dot",
+                 "R_in", "R_out", "xi_line", "lambda_line", "R_line", "xi_dt", "T_dt", "R_dt")
+GAMMAPY_UNITS = {"t_var": "s", "M_BH": "g", "m_dot": "g s-1", "R_in": "cm", "R_out": "cm",
+                 "lambda_line": "Angstrom", "R_line": "cm", "T_dt": "K", "R_dt": "cm"}
+
+
+@case("fit_gammapy_ec_blr_dt", sub=12, rtol=RTOL_EXP_TAIL)
+def _fit_gammapy(side, A, idx, store=None):
+    """ExternalComptonSpectralModel(n_e, ["blr", "dt"]).evaluate(energy, **kwargs): dN/dE in
+    1 / (cm2 eV s) (gammapy_wrapper.py:284-357)"""
+    pars = cases.c5_parameter_vectors(3, seed=7)
+    nu = cases.C5_NU if idx is None else cases.C5_NU[idx]
+    energy_eV = nu * orc.H_PLANCK / EV_ERG
+    if side == "orc":
+        d_L = store["fit_gammapy_ec_blr_dt__d_L"]
+        sed = np.stack([fit_oracle("ec_blr_dt", pars[i], nu, float(d_L[i])) for i in range(3)], axis=1)
+        return sed / (energy_eV[:, None] ** 2 * EV_ERG)
+    import importlib
+    if getattr(A, "is_product", False):
+        return A.fit_gammapy(["blr", "dt"], pars, energy_eV)
+    gw = importlib.import_module("agnpy.fit.gammapy_wrapper")
+    model = gw.ExternalComptonSpectralModel(A.agnpy.BrokenPowerLaw(), ["blr", "dt"])
+    out = []
+    for row in pars:
+        kwargs = {n: A.Q(v, GAMMAPY_UNITS.get(n, "")) for n, v in zip(GAMMAPY_NAMES, row)}
+        out.append(_val(model.evaluate(A.Q(energy_eV, "eV"), **kwargs)))
+    store["fit_gammapy_ec_blr_dt__d_L"] = np.array([float(importlib.import_module(
+        "astropy.coordinates").Distance(z=row[6]).to("cm").value) for row in pars])
+    return np.stack(out, axis=1)

@@ -411,7 +411,7 @@ def test_tau_on_synchrotron(kind):
     args = {"PowerLaw": (1e-2, 2.5, 10.0, 1e5), "BrokenPowerLaw": (1e-3, 2.0, 3.2, 1e3, 10.0, 1e6),
             "LogParabola": (1e-2, 2.2, 0.3, 1e3, 5.0, 1e6)}[kind]
     ne = ne_obj(kind, (args[0] * u.Unit("cm-3"),) + tuple(args[1:]))
-    blob = targets.Blob(1e16 * u.cm, 0.5, 1e28 * u.cm, 20, 20, 0.5 * u.G, ne)
+    blob = targets.Blob(1e16 * u.cm, 0.5, 20, 20, 0.5 * u.G, ne, d_L=1e28 * u.cm)
     nu = np.logspace(22, 31, 50)
     ref = orc.tau_on_synchrotron(nu, 0.5, 1e28, 20, 0.5, 1e16, kind, args, blob.gamma_e)
     got = ab.Absorption(blob, z=0.5).tau(nu * u.Hz)
@@ -431,7 +431,7 @@ def test_proton_synchrotron(integ):
     from agnpy_b200 import targets
     args = (1e-4, 2.2, 1.0, 1e9 / 0.938)          # proton power law, k p gamma_min gamma_max
     n_p = spectra.PowerLaw(*q_args(args))
-    blob = targets.Blob(1e16 * u.cm, 0.5, 1e28 * u.cm, 20, 20, 10 * u.G, spectra.PowerLaw(), n_p=n_p)
+    blob = targets.Blob(1e16 * u.cm, 0.5, 20, 20, 10 * u.G, spectra.PowerLaw(), n_p=n_p, d_L=1e28 * u.cm)
     nu = np.logspace(10, 30, 60)
     integrator = np.trapezoid if integ == "trapz" else ab.trapz_loglog
     got = ab.ProtonSynchrotron(blob, integrator=integrator).sed_flux(nu * u.Hz)
@@ -445,7 +445,7 @@ def test_ssc_energy_loss_rate():
     from agnpy_b200 import targets
     c = cases.case_c1()
     ne = ne_obj(c["ne_kind"], q_args(c["ne_args"]))
-    blob = targets.Blob(c["R_b"] * u.cm, c["z"], c["d_L"] * u.cm, c["delta_D"], 10, c["B"] * u.G, ne)
+    blob = targets.Blob(c["R_b"] * u.cm, c["z"], c["delta_D"], 10, c["B"] * u.G, ne, d_L=c["d_L"] * u.cm)
     gamma = np.logspace(0.5, 8.5, 77)
     got = ab.SynchrotronSelfCompton(blob).electron_energy_loss_rate(gamma)
     ref = orc.ssc_electron_energy_loss_rate(gamma, c["z"], c["d_L"], c["delta_D"], c["B"], c["R_b"],

@@ -82,26 +82,3 @@ def test_prefix_batch_and_large_gamma():
         c["R_line"] * u.cm, c["r"] * u.cm, *ne_tail(c), integrator=integ, gamma=c["gamma"],
         mu=c["mu"], phi=c["phi"]).value
     assert_parity(call(ab.trapz_prefix), cases.ORACLE_EC["blr"](c), what="prefix 1000 gamma")
-
-
-def test_fp32_integrand_opt_in(gold):
-    """AGNPY_INTEG_TRAPZ_FP32: FP32 point loop, FP64 masks / sums.  Stated tolerance 1e-5
-    (measured ~1e-6); exact zeros stay exact because the masks are still decided in FP64."""
-    worst = 0.0
-    for r in (1e16, 2e17, 1e18):
-        c = cases.case_c2(r=r)
-        got = ab.ExternalCompton.evaluate_sed_flux_blr(
-            *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_line"], c["epsilon_line"],
-            c["R_line"] * u.cm, c["r"] * u.cm, *ne_tail(c), integrator=ab.trapz_fp32,
-            gamma=c["gamma"], mu=c["mu"], phi=c["phi"]).value
-        ref = gold[f"c2_ec_blr_r{r:g}"]
-        assert_parity(got, ref, rtol=1e-5, what=f"fp32 C2 r={r:g}")
-        dev, _ = cases.max_rel_dev(got, ref)
-        worst = max(worst, dev)
-    assert worst > 1e-12, "suspiciously exact: is the FP32 kernel running?"
-    print(f"fp32 integrand: max rel dev vs oracle {worst:.2e}")
-    c = cases.case_c3_dt()
-    got = ab.ExternalCompton.evaluate_sed_flux_dt(
-        *ec_args(c), c["L_disk"] * u.Unit("erg s-1"), c["xi_dt"], c["epsilon_dt"], c["R_dt"] * u.cm,
-        c["r"] * u.cm, *ne_tail(c), integrator="trapz_fp32", gamma=c["gamma"], phi=c["phi"])
-    assert_parity(got.value, gold["c3_ec_dt"], rtol=1e-5, what="fp32 dt")

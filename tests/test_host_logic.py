@@ -119,18 +119,94 @@ def test_interpolated_distribution_table():
 
 
 def test_integrator_dispatch():
-    assert grids.integrator_code(np.trapezoid) == _lib.INTEG_TRAPZ
-    if hasattr(np, "trapz"):
-        assert grids.integrator_code(np.trapz) == _lib.INTEG_TRAPZ
+    """identity first: numpy's own trapz / trapezoid, this package's selectors, the strings; the
+    reference's function object by module + name; a user callable that merely shares a name must not
+    silently select a device rule"""
+    assert grids.integrator_code(grids.np_trapz) == _lib.INTEG_TRAPZ
+    for name in ("trapz", "trapezoid"):
+        if hasattr(np, name):
+            assert grids.integrator_code(getattr(np, name)) == _lib.INTEG_TRAPZ
+    assert grids.integrator_code(None) == _lib.INTEG_TRAPZ
     assert grids.integrator_code(ab.trapz_loglog) == _lib.INTEG_LOGLOG
+    assert grids.integrator_code(ab.trapz_prefix) == _lib.INTEG_TRAPZ_PREFIX
+    assert grids.integrator_code("trapz_loglog") == _lib.INTEG_LOGLOG
 
-    def trapz_loglog(y, x, axis=0):  # the reference's function is recognised by name
+    def trapz_loglog(y, x, axis=0):
         return None
+    with pytest.raises(ValueError):          # same name, not the reference's function
+        grids.integrator_code(trapz_loglog)
+    trapz_loglog.__module__ = "agnpy.utils.math"    # what the reference's function object carries
     assert grids.integrator_code(trapz_loglog) == _lib.INTEG_LOGLOG
+
+    def trapz(y, x, axis=0):
+        return None
+    with pytest.raises(ValueError):
+        grids.integrator_code(trapz)
     with pytest.raises(ValueError):
         grids.integrator_code(np.sum)
-    with pytest.raises(NotImplementedError):
-        ab.trapz_loglog(np.ones(3), np.arange(3))
+    with pytest.raises(ValueError):
+        grids.integrator_code("trapz_fp32")     # removed opt-in mode
+
+
+def test_trapz_loglog_is_a_callable_without_cpu_fallback():
+    """agnpy_b200.trapz_loglog(y, x, axis) integrates on the GPU (tests/test_gpu_parity.py); without
+    a CUDA device it fails loudly instead of computing on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.AgnpyB200Error):
+        ab.trapz_loglog(np.ones(3), np.arange(1.0, 4.0))
+    with pytest.raises(ValueError):
+        ab.trapz_loglog(np.ones((3, 4)), np.arange(1.0, 4.0), axis=1)
+
+
+def test_default_integrator_does_not_need_numpy_2():
+    """the drop-in signatures default to numpy.trapz by whichever name this numpy has (the reference
+    supports numpy >= 1.24, where np.trapezoid does not exist)"""
+    import inspect
+    for fn in (ab.Synchrotron.evaluate_sed_flux, ab.SynchrotronSelfCompton.evaluate_sed_flux,
+               ab.ExternalCompton.evaluate_sed_flux_blr, ab.ExternalCompton.evaluate_sed_flux_dt):
+        assert inspect.signature(fn).parameters["integrator"].default is grids.np_trapz
+    src = "".join((ROOT / "agnpy_b200" / f).read_text() for f in ("synchrotron.py", "compton.py"))
+    assert "np.trapezoid" not in src and "np.trapz" not in src
+
+
+def test_cosmology_known_answers():
+    """host d_L(z) helper against the reference's pinned numbers
+    (agnpy/emission_regions/tests/test_emission_regions.py:44-50, astropy Planck18)"""
+    from agnpy_b200 import cosmology, targets
+    assert cosmology.luminosity_distance(2.1) == pytest.approx(5.21497473e28, rel=1e-8)
+    assert cosmology.luminosity_distance(0.1) == pytest.approx(1.4682341e27, rel=1e-7)
+    z = np.array([0.1, 2.1, 0.1])
+    np.testing.assert_array_equal(cosmology.luminosity_distance(z),
+                                  [cosmology.luminosity_distance(float(v)) for v in z])
+    blob = targets.Blob(z=2.1)                      # reference signature: d_L from z
+    assert strip(blob.d_L, "cm") == pytest.approx(5.21497473e28, rel=1e-8)
+    assert targets.Blob(z=2.1, d_L=1e28 * u.cm).d_L.value == 1e28
+    with pytest.raises(ValueError):
+        targets.Blob(delta_D=-1)
+
+
+def test_fit_parameter_layout_matches_the_wrappers():
+    """scenario -> flat parameter names in the order the sherpa wrappers unpack them
+    (agnpy/fit/sherpa_wrapper.py:55, 83-98, 157-172, 233-251)"""
+    from agnpy_b200 import fit
+    from tests import cases
+    n = {sc: len(fit.parameter_names("BrokenPowerLaw", sc)) for sc in fit.SCENARIOS}
+    assert n == {"ssc": 10, "ec_blr": 20, "ec_dt": 20, "ec_blr_dt": 23}
+    full = fit.parameter_names("BrokenPowerLaw", "ec_blr_dt")
+    for sc, cols in cases.C5_COLUMNS.items():
+        assert fit.parameter_names("BrokenPowerLaw", sc) == tuple(full[c] for c in cols)
+    assert fit.scenario_of(None) == "ssc" and fit.scenario_of(["dt", "blr"]) == "ec_blr_dt"
+    pars = cases.c5_parameter_vectors(3)
+    models = fit.build_models(pars, None, "BrokenPowerLaw", "ec_blr_dt")
+    assert set(models) == {"synch", "ssc", "bb_disk", "ec_blr", "ec_dt", "bb_dt"}
+    from agnpy_b200 import cosmology
+    np.testing.assert_array_equal(models["synch"]["d_L"], cosmology.luminosity_distance(1.0))
+    np.testing.assert_allclose(models["ec_blr"]["R_b"],
+                               2.99792458e10 * 86400.0 * pars[:, 7] / 2.0, rtol=1e-15)
+    with pytest.raises(ValueError):
+        fit.build_models(pars[:, :22], None, "BrokenPowerLaw", "ec_blr_dt")
 
 
 def test_grid_validation():
@@ -154,7 +230,7 @@ def test_targets_and_blob_containers():
                           R_g_units=True)
     assert disk.R_in_tilde == 6 and strip(disk.R_out, "cm") / strip(disk.R_g, "cm") == pytest.approx(200)
     ne = spectra.PowerLaw(1e-8, 2.0, 10, 1e5)
-    blob = targets.Blob(1e16 * u.cm, 1.0, 2e28 * u.cm, 40, 40, 1 * u.G, ne)
+    blob = targets.Blob(1e16 * u.cm, 1.0, 40, 40, 1 * u.G, ne, d_L=2e28 * u.cm)
     assert blob.mu_s == pytest.approx((1 - 1 / 1600) / np.sqrt(1 - 1 / 1600))
     assert blob.gamma_e[0] == pytest.approx(10) and blob.gamma_e_external_frame.size == 200
     with pytest.raises(ValueError):
