@@ -25,6 +25,7 @@
 //   ec_finish_kernel                       fixed-order sum of the warp partials x prefactor
 //   run_ec                                 plan, scratch carving, launches
 #include <limits.h>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -835,6 +836,259 @@ __global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// np.trapz main path, v7: the same integrand, tables, masks and guard band as ec_main_poly_kernel,
+// with the work *around* the gamma loop restructured.  ncu on v6 (profiles/r1f_ec_main_poly_full.txt,
+// per (warp, nu) unit): 800 DFMA (1600 FP64-pipe cycles) but 2930 cycles of SMSP time; 545 of the
+// 740 other instructions sit outside the loop and collect 48 % of the stall samples -- serial
+// shared-memory probes of the window search (all 32 lanes walking the same entries), two loads and
+// a dozen ALU operations per pair for the guard band, a 5-step shuffle reduction per frequency, and
+// global loads of the pair weights.  A non-FP64 instruction costs the sub-partition a dispatch
+// slot the DFMA stream cannot use (scripts/micro/fp64_mix.cu), so each one removed is worth its
+// share of the run time.  Here:
+//   * window search by lane-parallel probes: lane l tests entry k0 + l, one ballot gives the index
+//     (two independent loads per frequency instead of >= 4 dependent ones; the first frequency of a
+//     chunk uses a 32-way search, 2 round trips at 200 gammas);
+//   * one loop over the window entries [wlo-1, whi] does both the per-pair index count and the
+//     guard-band test (no per-pair loads);
+//   * pair weights live in registers; dead pairs carry W = b = 0 and need no special casing;
+//   * the (mu, phi) partial sums of the L frequencies of a chunk are parked in shared memory and
+//     reduced once per block (8 values per lane + 2 shuffles) instead of once per frequency;
+//   * J = 8 pairs per thread at 64 threads per block keep the 512-pair slices of the folded table
+//     (2500 pairs -> 5 slices) while halving the number of (warp, nu) units; ACC2 gives each pair
+//     two accumulator chains where J = 4 leaves the 8-cycle DFMA latency exposed.
+// ---------------------------------------------------------------------------------------------
+// first k in [0, n] with G_k <= c (G descending), all lanes cooperating: 32 probes per round
+__device__ __forceinline__ int ec_warp_first_le(const long long* __restrict__ s_Gi, int n, long long c,
+                                                int lane) {
+    int lo = 0, len = n;
+    while (len > 0) {
+        const int s = (len + 31) >> 5;
+        const int k = lo + lane * s;
+        const bool gt = k < lo + len && s_Gi[k] > c;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, gt));
+        if (cnt == 0) return lo;
+        const int end = lo + len;
+        lo += (cnt - 1) * s + 1;  // the last probe that was still > c, plus one
+        if (s == 1) return lo;
+        len = min(s - 1, end - lo);
+    }
+    return lo;
+}
+// the same index for the next frequency's table, given the previous one (indices move by a few
+// entries per frequency step): probes at k_prev - 1 + lane; anything else -> full search
+__device__ __forceinline__ int ec_warp_step_le(const long long* __restrict__ s_Gi, int n, long long c,
+                                               int k_prev, int lane) {
+    const int k = k_prev - 1 + lane;
+    const bool gt = k < 0 || (k < n && s_Gi[k] > c);
+    const unsigned bal = __ballot_sync(0xffffffffu, gt);
+    const int cnt = __ffs(~bal) - 1;  // length of the run of set bits from lane 0 (-1: all 32 set)
+    if ((bal & 1u) && cnt > 0) return k_prev - 1 + cnt;
+    return ec_warp_first_le(s_Gi, n, c, lane);
+}
+
+template <int J, int T, bool ACC2, int MINB>
+__global__ void __launch_bounds__(T, MINB) ec_main_poly7_kernel(
+    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
+    const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma,
+    const double* __restrict__ rows, const double* __restrict__ ang, int n_pairs, int S, int L_nu,
+    double* __restrict__ part) {
+    extern __shared__ __align__(16) double sh[];  // L_nu rows | L_nu x (T+1) partial sums | L_nu mbarriers
+    constexpr int W_per_block = T >> 5;
+    const int slice = blockIdx.x, m = blockIdx.z;
+    const int i0 = blockIdx.y * L_nu, i1 = min(i0 + L_nu, n_nu);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row_words = ec_row_words(n_gamma);
+    double* s_sum = sh + (size_t)L_nu * row_words;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_sum + (size_t)L_nu * (T + 1));
+    if (tid == 0) {
+        for (int r = 0; r < i1 - i0; ++r) mbar_init(bars + r, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    const double* g_rows = rows + (size_t)m * n_nu * row_words;
+    if (tid == 0) {  // all rows of this block's frequency chunk, one bulk copy each
+        const unsigned row_bytes = (unsigned)row_words * sizeof(double);
+        for (int r = 0; r < i1 - i0; ++r) {
+            mbar_expect_tx(bars + r, row_bytes);
+            bulk_copy_g2s(sh + (size_t)r * row_words, g_rows + (size_t)(i0 + r) * row_words, row_bytes,
+                          bars + r);
+        }
+    }
+    const double* g_gm = gt + (size_t)m * 5 * n_gamma;
+    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
+    const double* a_omc = a_eps + n_pairs;
+    const double* a_b = a_omc + n_pairs;
+    const double* a_W = a_b + n_pairs;
+    const double* a_c = a_W + n_pairs;
+    const double* a_omc_p = a_c + n_pairs;  // mirror partner of a folded pair (W_p = 0: none)
+    const double* a_W_p = a_omc_p + n_pairs;
+    const int klo = hull[2 * m], khi = hull[2 * m + 1];  // non-zero range of n_e
+    const int jbase = (slice * T + tid) * J;
+
+    double b[J], b2[J], W[J];
+    int hc[J];  // high word of c; INT_MAX marks a pair that never contributes (W = b = 0)
+    unsigned always_doubt = 0;  // non-finite c: always decided by the reference's own formula
+    long long cmax = -1, cmin = LLONG_MAX;  // bits of c over the live pairs of the warp
+#pragma unroll
+    for (int jj = 0; jj < J; ++jj) {
+        const int j = jbase + jj;
+        const double c = j < n_pairs ? a_c[j] : -1.0;
+        const bool live = c > 0.0;  // false for NaN as well
+        b[jj] = live ? a_b[j] : 0.0;
+        b2[jj] = b[jj] * b[jj];
+        W[jj] = live ? a_W[j] : 0.0;
+        const long long ci = live ? __double_as_longlong(c) : -1LL;
+        hc[jj] = live ? (int)(ci >> 32) : INT_MAX;
+        if (live) {
+            cmax = max(cmax, ci);
+            cmin = min(cmin, ci);
+            if (hc[jj] >= 0x7ff00000) always_doubt |= 1u << jj;
+        }
+    }
+    cmax = warp_max_ll(cmax);
+    cmin = warp_min_ll(cmin);
+    const bool warp_live = cmax > 0 && khi >= 0;
+    int wlo = 0, whi = 0;  // first k with G_k <= cmax / <= cmin for the current frequency
+    for (int i = i0; i < i1; ++i) {
+        const int r = i - i0;
+        // warps run through the chunk independently: the only wait is for row i to have landed
+        mbar_wait(bars + r, 0);
+        const double* s_row = sh + (size_t)r * row_words;
+        const double2* s_QR = reinterpret_cast<const double2*>(s_row);
+        const long long* s_Gi = reinterpret_cast<const long long*>(s_row + 2 * (n_gamma + kRowPad));
+        const int* s_Gh = reinterpret_cast<const int*>(s_Gi);  // [2k+1] = high word
+        const double* s_SP = s_row + 2 * (n_gamma + kRowPad) + n_gamma;
+        double thread_sum = 0.0;
+        if (warp_live) {
+            // warp-uniform index window [wlo, whi]: every live pair's first unmasked index lies in it
+            if (r == 0) {
+                wlo = ec_warp_first_le(s_Gi, n_gamma, cmax, lane);
+                whi = ec_warp_first_le(s_Gi, n_gamma, cmin, lane);
+            } else {
+                wlo = ec_warp_step_le(s_Gi, n_gamma, cmax, wlo, lane);
+                whi = ec_warp_step_le(s_Gi, n_gamma, cmin, whi, lane);
+            }
+            // one pass over the window entries: per pair lo = wlo + #{k in [wlo, whi) : G_k > c}
+            // (G descending: a prefix count, on high words; a tie there is inside the guard band), and
+            // the guard band itself: an entry within 3 units of the high word of c (>= 1.4e-6
+            // relative) next to the index -> decide that pair with the reference's own formula
+            int lo[J];
+            unsigned doubt = always_doubt;
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) lo[jj] = wlo;
+            {
+                const int ka = max(wlo - 1, 0), kb = min(whi, n_gamma - 1);
+                for (int k = ka; k <= kb; ++k) {
+                    const int gh = s_Gh[2 * k + 1];
+                    const int inside = (k >= wlo && k < whi) ? 1 : 0;
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) {
+                        const int d = gh - hc[jj];
+                        lo[jj] += (d > 0) ? inside : 0;
+                        if ((unsigned)(d + 3) <= 6u) doubt |= 1u << jj;
+                    }
+                }
+            }
+            const int2 ill = *reinterpret_cast<const int2*>(s_SP + n_gamma + 1);
+            if (max(wlo - 1, 0) < ill.y && min(whi, n_gamma - 1) >= ill.x) {  // ill-conditioned G in the window
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj)
+                    if (hc[jj] != INT_MAX) doubt |= 1u << jj;
+            }
+            int kbeg = wlo, kmid = whi;  // lo[jj] lies in [wlo, whi] unless re-decided below
+            double fold_corr = 0.0;      // see below; almost always 0
+            if (__any_sync(0xffffffffu, doubt != 0)) {  // rare
+                int tmin = INT_MAX, tmax = 0;
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    if (doubt & (1u << jj)) {
+                        const int j = jbase + jj;
+                        lo[jj] = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc, j, nu[i], models[m].z);
+                        // folded pair: the mirror partner takes its own decision.  If it starts
+                        // at another index, the shared evaluation (weight W + W_p from lo) is off
+                        // by W_p times the integrand steps between the two indices.
+                        const double W_p = a_W_p[j];
+                        if (W_p != 0.0) {
+                            const int lo_p = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc_p, j, nu[i],
+                                                                   models[m].z);
+                            const int ka = max(min(lo[jj], lo_p), klo), kb = min(max(lo[jj], lo_p), khi + 1);
+                            double d = 0.0;
+                            for (int k = ka; k < kb; ++k) {
+                                const double2 qr = s_QR[k];
+                                d += (s_SP[k] - s_SP[k + 1]) + fma(qr.y, b[jj], qr.x * b2[jj]);
+                            }
+                            fold_corr += (lo_p < lo[jj]) ? W_p * d : -(W_p * d);
+                        }
+                    }
+                    if (hc[jj] != INT_MAX) { tmin = min(tmin, lo[jj]); tmax = max(tmax, lo[jj]); }
+                }
+                kbeg = __reduce_min_sync(0xffffffffu, tmin);
+                kmid = __reduce_max_sync(0xffffffffu, tmax);
+            }
+            kbeg = max(kbeg, klo);
+            kmid = min(max(kmid, kbeg), khi + 1);
+            double acc[J], acc_r[ACC2 ? J : 1];
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) acc[jj] = 0.0;
+            if (ACC2) {
+#pragma unroll
+                for (int jj = 0; jj < (ACC2 ? J : 1); ++jj) acc_r[jj] = 0.0;
+            }
+            // phase 1 (a few steps: the pairs of a warp are neighbours in c): lanes join as the
+            // loop passes their first unmasked index
+            for (int k = kbeg; k < kmid; ++k) {
+                const double2 qr = s_QR[k];
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj)
+                    if (k >= lo[jj]) acc[jj] = fma(qr.y, b[jj], fma(qr.x, b2[jj], acc[jj]));
+            }
+            // phase 2: every live lane is above its gamma_min -> 2 DFMA per integrand point;
+            // four gamma steps per trip and no remainder loop: the row carries kRowPad zero entries
+            // after the last index, so running past khi adds exact zeros
+            for (int k = kmid; k <= khi; k += 4) {
+                const double2 q0 = s_QR[k], q1 = s_QR[k + 1], q2 = s_QR[k + 2], q3 = s_QR[k + 3];
+#define EC_STEP(q)                                                                       \
+    _Pragma("unroll") for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q.x, b2[jj], acc[jj]); \
+    if (ACC2) {                                                                           \
+        _Pragma("unroll") for (int jj = 0; jj < J; ++jj)                                  \
+            acc_r[ACC2 ? jj : 0] = fma(q.y, b[jj], acc_r[ACC2 ? jj : 0]);                 \
+    } else {                                                                              \
+        _Pragma("unroll") for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q.y, b[jj], acc[jj]); \
+    }
+                EC_STEP(q0) EC_STEP(q1) EC_STEP(q2) EC_STEP(q3)
+#undef EC_STEP
+            }
+            // every pair adds the b-independent suffix sum at its own first unmasked index (both are
+            // exactly 0 past the last electron index); dead pairs have W = 0
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                const double a = ACC2 ? acc[jj] + acc_r[ACC2 ? jj : 0] : acc[jj];
+                thread_sum = fma(W[jj], a + s_SP[min(max(lo[jj], klo), n_gamma)], thread_sum);
+            }
+            thread_sum += fold_corr;
+        }
+        s_sum[(size_t)r * (T + 1) + tid] = thread_sum;
+    }
+    // per warp: sum its 32 columns of every frequency row.  Lane l takes row l % 8 (+8, +16, ...),
+    // a quarter of the columns each, then two shuffle steps join the quarters.
+    __syncwarp();
+    const int n_rows = i1 - i0;
+    for (int r0 = 0; r0 < n_rows; r0 += 8) {
+        const int r = r0 + (lane & 7), q = lane >> 3;
+        double v = 0.0;
+        if (r < n_rows) {
+            const double* col = s_sum + (size_t)r * (T + 1) + warp * 32 + q * 8;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) v += col[x];
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (q == 0 && r < n_rows)
+            part[(((size_t)m * n_nu + i0 + r) * S + slice) * W_per_block + warp] = v;
+    }
+}
+
 // prefactor of each evaluate_sed_flux_* (external_compton.py:133-142, 229-240, 361-373, 476-490,
 // 590-600), in the reference's operation order
 __device__ __forceinline__ double ec_prefactor(int variant, const agnpy_model_t& M, double nu_i) {
@@ -887,100 +1141,163 @@ __global__ void __launch_bounds__(128) ec_finish_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Opt-in fast path for the np.trapz integrator (AGNPY_INTEG_TRAPZ_PREFIX).  With np.trapz the
-// gamma integral is a fixed weighted sum and the kernel is a quadratic in b:
-//     sum_{k>=k0} wf_k K_k = SP[k0] + b^2 SQ[k0] - 2 b SR[k0],
-//     P_k = wf_k A_k,  Q_k = wf_k G_k^2,  R_k = wf_k G_k,   S*[k] = suffix sums over k..khi,
-// so a (nu, model) needs one suffix scan of three length-n_gamma arrays and, per (mu,phi) pair,
-// the mask index k0 plus four FP64 instructions: O(n_gamma + n_pairs log n_gamma) instead of
-// O(n_gamma n_pairs).  Same integral, same grid, same masks (k0 is found exactly as in the direct
-// kernel); only the association order of the gamma sum differs (~1e-15 relative).
-// grid = (n_nu, n_models), 256 threads; the prefactor is applied in-kernel.
+// Opt-in fast path for the np.trapz integrator (AGNPY_INTEG_TRAPZ_PREFIX): the (mu, phi) sum taken
+// *before* the gamma sum.  With np.trapz the integrand of a (nu, model) is a fixed weighted double
+// sum, and each point is a polynomial in the pair variable b:
+//     sum_j W_j sum_{k >= lo_j} (P_k + Q_k b_j^2 + R_k b_j)
+//   = sum_k [ P_k M0(n_k) + Q_k M2(n_k) + R_k M1(n_k) ],      n_k = #{ j : pair j unmasked at gamma_k },
+//     M0(n) = sum_{j<n} W_j,  M1(n) = sum_{j<n} W_j b_j,  M2(n) = sum_{j<n} W_j b_j^2
+// over the pairs sorted by descending threshold c_j: the unmasked pairs at gamma_k are exactly a
+// prefix of that order (pair j is unmasked iff G_k <= c_j).  The three prefix moments do not depend on
+// the frequency, so a (nu, model) costs one binary search per gamma point and segment instead of
+// one DFMA pair per (gamma, mu, phi) point: O(n_gamma log n_pairs) instead of O(n_gamma n_pairs).
+// Same integral, same grids, same masks -- the guard band is the one of the direct kernel: pairs
+// whose threshold lies within 3 units of the high word of G_k (>= 1.4e-6 relative) are taken out
+// of the prefix and decided one by one with the reference's own formula (kernels.py:36-40), mirror
+// partners of a folded phi axis separately -- only the association order of the sums differs
+// (measured <= 1e-13 from the oracle, tests/test_gpu_prefix.py).
+//
+// ec_moments_kernel: grid = (segments, models), 1024 threads: exclusive prefix sums of W, W b, W b^2
+//                    over each sorted 1024-pair segment + the high words of c (dead pairs: INT_MIN)
+// ec_moment_kernel:  grid = (nu / 8, models), 256 threads over the (gamma, nu) items of 8 frequencies:
+//                    y, A, G, P, Q, R of kernels.py:61-65 in the operation order of the table
+//                    kernels, the search (sorted high words staged in shared memory), the band, a
+//                    fixed-order sum per frequency and the prefactor.  No per-(nu, model) rows are
+//                    written or read.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ec_prefix_kernel(
-    int variant, const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
-    const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma, int search_iters,
-    const double2* __restrict__ nt, const double* __restrict__ ang, int n_pairs,
-    double* __restrict__ sed) {
-    extern __shared__ double sh[];
-    __shared__ double red[32];
-    const int i = blockIdx.x, m = blockIdx.y;
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* g_gm = gt + (size_t)m * 5 * n_gamma;
-    const double* g_f = g_gm + n_gamma;
-    const double2* AG = nt + ((size_t)m * n_nu + i) * n_gamma;
-    const int klo = hull[2 * m], khi = hull[2 * m + 1];
-    double* s_G = sh;                  // [n]
-    double* s_A = s_G + n_gamma;       // [n]
-    double* s_S = s_A + n_gamma;       // [3][n+1] suffix sums of P, Q, R
-    const int n1 = n_gamma + 1;
-    for (int k = tid; k < n_gamma; k += T) {
-        double2 ag = AG[k];
-        double wf = g_f[k];
-        bool live = k >= klo && k <= khi && ag.y < kFmax;
-        double R = live ? wf * ag.y : 0.0;
-        s_G[k] = ag.y;
-        s_A[k] = ag.x;
-        s_S[k] = live ? wf * ag.x : 0.0;
-        s_S[n1 + k] = R * (live ? ag.y : 0.0);
-        s_S[2 * n1 + k] = R;
-    }
-    if (tid < 3) s_S[tid * n1 + n_gamma] = 0.0;
-    __syncthreads();
-    // suffix scan: warp w < 3 scans array w; lane l owns a contiguous chunk, highest k first
-    if (warp < 3) {
-        double* a = s_S + warp * n1;
-        const int chunk = (n_gamma + 31) / 32;
-        const int hi = n_gamma - lane * chunk, lo = max(hi - chunk, 0);  // lane 0 owns the top chunk
-        double run = 0.0;
-        for (int k = hi - 1; k >= lo; --k) { run += a[k]; a[k] = run; }
-        if (hi <= 0) run = 0.0;
-        // exclusive prefix over lanes (lane 0 = top chunk): offset = sum of totals of lanes < l
-        double incl = run;
+constexpr int kMomStride = kPairSeg + 1;
+__global__ void __launch_bounds__(kPairSeg) ec_moments_kernel(const double* __restrict__ ang, int n_pairs,
+                                                              int n_seg, double* __restrict__ mom,
+                                                              int* __restrict__ hcs) {
+    __shared__ double s_w[3][32];
+    const int m = blockIdx.y, seg = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const double* row = ang + (size_t)m * kAngCols * n_pairs;
+    const int j = seg * kPairSeg + t;
+    const bool in = j < n_pairs;
+    const double c = in ? row[4 * (size_t)n_pairs + j] : -1.0;
+    const bool live = c > 0.0;  // false for NaN
+    const double b = live ? row[2 * (size_t)n_pairs + j] : 0.0, W = live ? row[3 * (size_t)n_pairs + j] : 0.0;
+    if (in) hcs[(size_t)m * n_pairs + j] = live ? (int)(__double_as_longlong(c) >> 32) : INT_MIN;
+    double v[3] = {W, W * b, (W * b) * b};
+    double incl[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double x = v[q];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            double v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            double y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
         }
-        double offset = incl - run;
-        for (int k = hi - 1; k >= lo; --k) a[k] += offset;
+        incl[q] = x;
+        if (lane == 31) s_w[q][warp] = x;
     }
     __syncthreads();
-    const double* SP = s_S;
-    const double* SQ = s_S + n1;
-    const double* SR = s_S + 2 * n1;
+    if (warp < 3) {  // exclusive scan of the 32 warp totals of quantity `warp`
+        double tot = s_w[warp][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double y = __shfl_up_sync(0xffffffffu, tot, o);
+            if (lane >= o) tot += y;
+        }
+        // exclusive = the inclusive value of the lane below (never `tot - own`: the moments of one
+        // warp can exceed everything before it by 20 decades -- pairs seen almost tail-on have b ~ 1e14)
+        const double excl = __shfl_up_sync(0xffffffffu, tot, 1);
+        s_w[warp][lane] = lane ? excl : 0.0;
+    }
+    __syncthreads();
+    double* out = mom + ((size_t)m * n_seg + seg) * 3 * kMomStride;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        out[q * kMomStride + t + 1] = incl[q] + s_w[q][warp];
+        if (t == 0) out[q * kMomStride] = 0.0;
+    }
+}
+
+constexpr int kMomNu = 8;  // frequencies per block, at most (one warp each in the final sums)
+__global__ void __launch_bounds__(256) ec_moment_kernel(
+    int variant, const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
+    const double* __restrict__ gamma, const double* __restrict__ gt, const int* __restrict__ hull,
+    int n_gamma, const double* __restrict__ ang, int n_pairs, int n_seg, const double* __restrict__ mom,
+    const int* __restrict__ hcs, int hc_in_smem, int L, double* __restrict__ sed) {
+    extern __shared__ double sh_mom[];  // L x n_k item values, then (optionally) the sorted high words
+    const int i0 = blockIdx.x * L, m = blockIdx.y, tid = threadIdx.x;
+    const int n_loc = min(L, n_nu - i0);
+    const agnpy_model_t& M = models[m];
+    const double* g_f = gt + (size_t)m * 5 * n_gamma + n_gamma;  // w_k N_e / gamma_k^2
+    const int klo = hull[2 * m], khi = hull[2 * m + 1];
+    const int n_k = khi >= klo ? khi - klo + 1 : 0;
     const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
     const double* a_omc = a_eps + n_pairs;
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
-    const double* a_c = a_W + n_pairs;
-    double acc = 0.0;
-    for (int j = tid; j < n_pairs; j += T) {
-        const double cj = a_c[j], b = a_b[j], W = a_W[j];
-        if (!(cj > 0.0)) continue;
-        int lo = 0, hi = n_gamma;
-        for (int it = 0; it < search_iters; ++it) {
-            int mid = (lo + hi) >> 1;
-            bool open = lo < hi;
-            bool le = s_G[min(mid, n_gamma - 1)] <= cj;
-            hi = (open && le) ? mid : hi;
-            lo = (open && !le) ? mid + 1 : lo;
-        }
-        int k = lo;
-        const double band = 1e-6 * cj;
-        int ka = min(k, n_gamma - 1), kb = max(k - 1, 0);
-        double Ga = s_G[ka], Aa = s_A[ka], Gb = s_G[kb], Ab = s_A[kb];
-        bool doubt = (k < n_gamma && (fabs(Ga - cj) <= band || Aa > 1e8)) ||
-                     (k > 0 && (fabs(Gb - cj) <= band || (Ab > 1e8 && Gb < kFmax))) || !(cj < kFmax);
-        if (doubt)
-            k = first_unmasked_exact(g_gm, n_gamma, a_eps[j], nu_to_eps(nu[i], models[m].z, 1.0), a_omc[j]);
-        k = max(k, klo);
-        if (k > khi || khi < 0) continue;
-        double I = fma(b, fma(b, SQ[k], -2.0 * SR[k]), SP[k]);
-        acc = fma(W, I, acc);
+    const double* a_omc_p = a_W + 2 * (size_t)n_pairs;
+    const double* a_W_p = a_omc_p + n_pairs;
+    const double* mm = mom + (size_t)m * n_seg * 3 * kMomStride;
+    double* s_val = sh_mom;
+    const int* hc = hcs + (size_t)m * n_pairs;
+    if (hc_in_smem) {
+        int* s_hc = reinterpret_cast<int*>(sh_mom + (size_t)L * (n_gamma + 1));
+        for (int j = tid; j < n_pairs; j += blockDim.x) s_hc[j] = hc[j];
+        hc = s_hc;
+        __syncthreads();
     }
-    acc = block_sum(acc, red);
-    if (tid == 0) sed[(size_t)m * n_nu + i] = ec_prefactor(variant, models[m], nu[i]) * acc;
+    // one item per (gamma index, local frequency)
+    for (int item = tid; item < n_k * n_loc; item += blockDim.x) {
+        const int q = item / n_k, k = klo + (item - q * n_k);
+        // EC uses nu_to_epsilon_prime(nu, z) without the Doppler factor (external_compton.py:123)
+        const double eps_s = nu_to_eps(nu[i0 + q], M.z, 1.0);
+        const double g = gamma[k];
+        const double y = 1.0 - eps_s / g;
+        double val = 0.0;
+        const double A = y + 1.0 / y;
+        const double G = eps_s / ((g * g) * y);
+        if (y > 0.0 && G < kFmax) {  // else gamma <= eps_s: G = +inf, no pair is unmasked
+            const double wf = g_f[k];
+            const double wG = wf * G;
+            const double P = wf * A, Q = wG * G, R = -2.0 * wG;
+            const bool ill = A > 1e8;  // y < 1e-8: G itself is ill-conditioned, decide every pair exactly
+            const int hG = (int)(__double_as_longlong(G) >> 32);
+            double M0 = 0.0, M1 = 0.0, M2 = 0.0, fix = 0.0;
+            for (int seg = 0; seg < n_seg; ++seg) {
+                const int j0 = seg * kPairSeg, cnt = min(kPairSeg, n_pairs - j0);
+                const int* h = hc + j0;
+                // first position whose high word is <= hG + 3: everything before it is surely unmasked
+                int lo = 0, hi = ill ? 0 : cnt;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (h[mid] > hG + 3) lo = mid + 1; else hi = mid;
+                }
+                const double* ms = mm + (size_t)seg * 3 * kMomStride;
+                M0 += ms[lo];
+                M1 += ms[kMomStride + lo];
+                M2 += ms[2 * kMomStride + lo];
+                // guard band (or every live pair of an ill-conditioned entry): the reference's decision
+                for (int p = lo; p < cnt && (ill ? h[p] != INT_MIN : h[p] >= hG - 3); ++p) {
+                    const int j = j0 + p;
+                    const double e = a_eps[j], b = a_b[j], W = a_W[j], W_p = a_W_p[j];
+                    const double f = P + fma(Q, b * b, R * b);
+                    double root = sqrt(1.0 + 2.0 / (e * eps_s * a_omc[j]));
+                    if (g >= eps_s / 2.0 * (1.0 + root)) fix += (W - W_p) * f;
+                    if (W_p != 0.0) {
+                        root = sqrt(1.0 + 2.0 / (e * eps_s * a_omc_p[j]));
+                        if (g >= eps_s / 2.0 * (1.0 + root)) fix += W_p * f;
+                    }
+                }
+            }
+            val = fma(Q, M2, fma(R, M1, P * M0)) + fix;
+        }
+        s_val[(size_t)q * (n_gamma + 1) + (k - klo)] = val;
+    }
+    __syncthreads();
+    // warp q sums the items of local frequency q in a fixed order: lanes stride the gamma axis,
+    // then the shuffle tree
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int q = warp; q < n_loc; q += blockDim.x >> 5) {
+        double acc = 0.0;
+        for (int x = lane; x < n_k; x += 32) acc += s_val[(size_t)q * (n_gamma + 1) + x];
+        acc = warp_sum(acc);
+        if (lane == 0) sed[(size_t)m * n_nu + i0 + q] = ec_prefactor(variant, M, nu[i0 + q]) * acc;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -999,16 +1316,12 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
     p.n_pairs = ec_n_pairs(variant, n_mu, n_phi);
     p.T = p.n_pairs <= 32 ? 32 : p.n_pairs <= 64 ? 64 : 128;
     p.J = 1;
-    // measured on B200 (scripts/tune_ec.py): 128 threads x 8 pairs is the fastest tile at the
-    // default 5000 pairs; smaller pair counts keep more, smaller tiles
     if (integ == AGNPY_INTEG_TRAPZ) {
-        p.J = p.n_pairs >= 2048 ? 8 : p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
-        // 8 pairs per thread run the gamma loop a little faster than 4, unless the last 1024-pair
-        // slice would be mostly padding (2500 folded pairs: 3 x 1024 wastes 19 %, 5 x 512 wastes 2 %)
-        if (p.J == 8) {
-            const int pad8 = (p.n_pairs + 1023) / 1024 * 1024, pad4 = (p.n_pairs + 511) / 512 * 512;
-            if (pad8 - pad4 > p.n_pairs / 12) p.J = 4;
-        }
+        p.J = p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
+        // polynomial kernel (>= 512 pairs): 64 threads x 8 consecutive sorted pairs = 512-pair slices
+        // (2500 folded pairs at the default grids -> 5 slices, 2 % padding), measured fastest on B200
+        // (scripts/tune_ec.py, profiles/r2*_tune_ec.txt)
+        if (p.n_pairs >= 512) { p.T = 64; p.J = 8; }
     }
     if (const char* e = getenv("AGNPY_B200_EC_PLAN")) {  // development knob: "T,J"
         int t = 0, j = 0;
@@ -1027,7 +1340,9 @@ static size_t ec_words(const EcPlan& p, int n_nu, int n_gamma) {
     return 5 * (size_t)n_gamma + 2      // gamma tables + hull (2 ints in one double slot, padded)
            + (kAngCols + kRawCols) * (size_t)p.n_pairs  // pair table (sorted) + unsorted values
            + 2 * (size_t)n_nu * n_gamma // {A,G}
-           + (size_t)n_nu * ec_row_words(n_gamma)  // polynomial rows (np.trapz path)
+           // polynomial rows (np.trapz path) or, in the same area, the prefix moments + sorted high words
+           + std::max((size_t)n_nu * ec_row_words(n_gamma),
+                      (size_t)((p.n_pairs + kPairSeg - 1) / kPairSeg) * 3 * kMomStride + p.n_pairs / 2 + 2)
            + (size_t)n_nu * p.S * p.W();
 }
 
@@ -1062,10 +1377,10 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
     // mirror-symmetric phi grid (the caller vouches for it): one table entry per mirror pair, if
     // the folded (mu, phi) table still feeds the polynomial kernel
-    if (fold_req && integ == AGNPY_INTEG_TRAPZ && !prefix && n_phi >= 2 &&
+    if (fold_req && integ == AGNPY_INTEG_TRAPZ && n_phi >= 2 &&
         (variant == AGNPY_EC_ISO_MONO || variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR)) {
         EcPlan pf = ec_plan(variant, n_mu, (n_phi + 1) / 2, integ);
-        if (pf.n_pairs >= 512) p = pf;
+        if (prefix || pf.n_pairs >= 512) p = pf;
     }
     const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
     // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
@@ -1075,14 +1390,16 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     // carve: {A,G} table first (16-byte aligned: ws comes from cudaMalloc), then the rest
     double2* nt = (double2*)ws;
     double* rows = (double*)(nt + M * n_nu * n_gamma);  // 16-byte aligned: even word counts
-    double* gt = rows + M * n_nu * ec_row_words(n_gamma);
+    double* gt = rows + M * std::max((size_t)n_nu * ec_row_words(n_gamma),
+                                     (size_t)((p.n_pairs + kPairSeg - 1) / kPairSeg) * 3 * kMomStride +
+                                         p.n_pairs / 2 + 2);
     double* ang = gt + M * 5 * n_gamma;
     double* raw = ang + M * kAngCols * p.n_pairs;
     double* part = raw + M * kRawCols * p.n_pairs;
     int* hull = (int*)(part + M * n_nu * p.S * p.W());
     {
         int nB = (p.n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;
-        dim3 grid(1 + nB + (v5 ? 0 : nC * n_nu), n_models);
+        dim3 grid(1 + nB + ((v5 || prefix) ? 0 : nC * n_nu), n_models);
         ec_tables_kernel<<<grid, 128, 0, stream>>>(variant, models, ne_kind, nu, n_nu, gamma, n_gamma,
                                                    mu, n_mu, phi, n_phi, ne_table, integ, p.n_pairs,
                                                    gt, hull, raw, nt);
@@ -1096,16 +1413,34 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         note_launch();
     }
     if (prefix) {
-        int iters = 1;
-        while ((1 << iters) < n_gamma + 1) ++iters;
-        size_t smem = (5 * (size_t)n_gamma + 3) * sizeof(double);
+        // prefix moments over the sorted segments (the `rows` area is free on this path), then one
+        // block per (nu, model)
+        const int n_seg = (p.n_pairs + kPairSeg - 1) / kPairSeg;
+        int sms_prefix = 148;
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms_prefix, cudaDevAttrMultiProcessorCount, dev);
+        }
+        double* mom = rows;
+        int* hcs = (int*)(mom + M * n_seg * 3 * kMomStride);
+        dim3 gm(n_seg, n_models);
+        ec_moments_kernel<<<gm, kPairSeg, 0, stream>>>(ang, p.n_pairs, n_seg, mom, hcs);
+        note_launch();
+        // frequencies per block: 8 once that still leaves a few waves of blocks, fewer for small calls
+        int L = kMomNu;
+        while (L > 1 && (long long)((n_nu + L - 1) / L) * n_models < 4LL * sms_prefix) L >>= 1;
+        dim3 grid((n_nu + L - 1) / L, n_models);
+        size_t smem = (size_t)L * (n_gamma + 1) * sizeof(double);
+        const size_t hc_bytes = (size_t)p.n_pairs * sizeof(int);
+        const int hc_in_smem = smem + hc_bytes <= 96 * 1024;  // the sorted high words, if they fit
+        if (hc_in_smem) smem += hc_bytes;
         if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma too large for the EC prefix kernel");
         if (smem > 48 * 1024)
-            cudaFuncSetAttribute(ec_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid(n_nu, n_models);
+            cudaFuncSetAttribute(ec_moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         timing_begin(stream);
-        ec_prefix_kernel<<<grid, 256, smem, stream>>>(variant, models, nu, n_nu, gt, hull, n_gamma, iters,
-                                                      nt, ang, p.n_pairs, sed);
+        ec_moment_kernel<<<grid, 256, smem, stream>>>(variant, models, nu, n_nu, gamma, gt, hull, n_gamma,
+                                                      ang, p.n_pairs, n_seg, mom, hcs, hc_in_smem, L, sed);
         timing_end(stream);
         note_launch();
         return check_last("ec_sed (prefix)");
@@ -1139,23 +1474,45 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
             if (v >= 1) L_nu = v;
         }
         const size_t row_bytes = (size_t)row_words * sizeof(double);
-        while (L_nu > 1 && L_nu * row_bytes > 52 * 1024) L_nu >>= 1;  // 4 blocks of rows per SM
+        const bool v6 = getenv("AGNPY_B200_EC_V6") != nullptr;  // A/B knob: the round-1 kernel
+        const bool acc2 = getenv("AGNPY_B200_EC_ACC2") != nullptr;
+        // shared memory per block: rows (+ parked partial sums and barriers); keep >= 4 blocks per SM
+        const size_t per_nu = row_bytes + 8 + (v6 ? 0 : (size_t)(p.T + 1) * sizeof(double));
+        // (4 blocks of 128 threads, 6 of 64 threads x 8 pairs, 8 of 64 x 4: the register-limited counts)
+        const int blocks_per_sm = getenv("AGNPY_B200_EC_MINB5") ? 5 : (v6 || p.T >= 128) ? 4 : (p.J == 8 ? 6 : 8);
+        const size_t smem_cap = (size_t)(227 * 1024) / blocks_per_sm - 1024;
+        if (v6) { while (L_nu > 1 && L_nu * per_nu > smem_cap) L_nu >>= 1; }
+        else if (L_nu * per_nu > smem_cap) L_nu = (int)std::max<size_t>(1, smem_cap / per_nu);
         dim3 grid(p.S, (n_nu + L_nu - 1) / L_nu, n_models);
-        const size_t smem6 = L_nu * (row_bytes + 8);
+        const size_t smem6 = L_nu * per_nu;
         timing_begin(stream);
-#define EC_LAUNCH6(JJ)                                                                             \
-    do {                                                                                           \
-        if (smem6 > 48 * 1024)                                                                     \
-            cudaFuncSetAttribute(ec_main_poly_kernel<JJ>,                                          \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);         \
-        ec_main_poly_kernel<JJ><<<grid, p.T, smem6, stream>>>(models, nu, n_nu, gt, hull, n_gamma,  \
-                                                             rows, ang, p.n_pairs, p.S, L_nu, part); \
+#define EC_LAUNCH_K(KERNEL)                                                                         \
+    do {                                                                                            \
+        if (smem6 > 48 * 1024)                                                                      \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);  \
+        KERNEL<<<grid, p.T, smem6, stream>>>(models, nu, n_nu, gt, hull, n_gamma, rows, ang,        \
+                                             p.n_pairs, p.S, L_nu, part);                           \
     } while (0)
-        if (p.J == 8) EC_LAUNCH6(8);
-        else if (p.J == 4) EC_LAUNCH6(4);
-        else if (p.J == 2) EC_LAUNCH6(2);
-        else EC_LAUNCH6(1);
-#undef EC_LAUNCH6
+        if (v6 && p.T == 128) {
+            if (p.J == 8) EC_LAUNCH_K(ec_main_poly_kernel<8>);
+            else if (p.J == 4) EC_LAUNCH_K(ec_main_poly_kernel<4>);
+            else if (p.J == 2) EC_LAUNCH_K(ec_main_poly_kernel<2>);
+            else EC_LAUNCH_K(ec_main_poly_kernel<1>);
+        } else if (p.T == 64 && p.J == 8) {
+            EC_LAUNCH_K((ec_main_poly7_kernel<8, 64, false, 6>));
+        } else if (p.T == 64 && p.J == 4) {
+            if (acc2) EC_LAUNCH_K((ec_main_poly7_kernel<4, 64, true, 8>));
+            else EC_LAUNCH_K((ec_main_poly7_kernel<4, 64, false, 8>));
+        } else if (p.T == 128 && p.J == 8) {
+            EC_LAUNCH_K((ec_main_poly7_kernel<8, 128, false, 3>));
+        } else if (p.T == 128 && p.J == 4) {
+            if (acc2) EC_LAUNCH_K((ec_main_poly7_kernel<4, 128, true, 4>));
+            else if (getenv("AGNPY_B200_EC_MINB5")) EC_LAUNCH_K((ec_main_poly7_kernel<4, 128, false, 5>));
+            else EC_LAUNCH_K((ec_main_poly7_kernel<4, 128, false, 4>));
+        } else {
+            return fail(AGNPY_ERR_ARG, "ec_sed: unsupported AGNPY_B200_EC_PLAN for the polynomial kernel");
+        }
+#undef EC_LAUNCH_K
         timing_end(stream);
         note_launch();
         dim3 g2((n_nu + 127) / 128, n_models);

@@ -13,8 +13,13 @@ inside the timed step.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
 ranks); `e2e` goes through the public host-buffer API (pinned H2D of the model table, D2H of
-the SEDs, wall clock); `roofline` is for the dominant kernel ec_main_poly_kernel; `cpu_baseline` is
-the oracle (reference arithmetic, 1 core) timed on this box.
+the SEDs, wall clock); `roofline` is for the dominant kernel (ec_main_poly7_kernel): `frac` is the
+EXECUTED FP64 work over the measured DFMA peak, the nominal 16 flop/point figure of SURVEY 8(a) is
+kept beside it as `algorithmic`; `cpu_baseline` is the reference's own code (agnpy v0.5.0 from
+baseline/_ref, on the miniature astropy of oracle/astropy_stub) on one core of this box, or the
+oracle port where the reference install did not travel.  `extra` carries, at every N, the two
+strong-scaling workloads of BASELINE.json: configs[4] (65 536 fit parameter vectors in total) and
+configs[3] (one 2e10-point SED, frequency-sharded).
 """
 import argparse
 import json
@@ -74,6 +79,41 @@ def oracle_sed(model, g, nu=None):
                                model["R_b"], model["tgt"][0], model["tgt"][1], model["tgt"][2],
                                model["tgt"][3], model["tgt"][4], "BrokenPowerLaw",
                                tuple(model["ne"][:6]), gamma=g["gamma"], mu=g["mu"], phi=g["phi"])
+
+
+def reference_module():
+    """the unmodified reference (agnpy v0.5.0) if its offline install travelled with the repo
+    (baseline/_ref) or its checkout is present; None otherwise"""
+    try:
+        from oracle import reference_loader
+        if not reference_loader.available():
+            return None
+        return reference_loader.load()
+    except Exception:
+        return None
+
+
+def reference_sed(agnpy, model, g, nu=None):
+    """ExternalCompton.evaluate_sed_flux_blr of the reference itself (external_compton.py:398-490),
+    Quantities in and out"""
+    import astropy.units as u
+    nu = g["nu"] if nu is None else nu
+    t = model["tgt"]
+    ne = model["ne"]
+    with np.errstate(all="ignore"):
+        sed = agnpy.ExternalCompton.evaluate_sed_flux_blr(
+            nu * u.Hz, float(model["z"]), float(model["d_L"]) * u.cm, float(model["delta_D"]),
+            float(model["mu_s"]), float(model["R_b"]) * u.cm, float(t[0]) * u.Unit("erg s-1"),
+            float(t[1]), float(t[2]), float(t[3]) * u.cm, float(t[4]) * u.cm, agnpy.BrokenPowerLaw,
+            float(ne[0]) * u.Unit("cm-3"), *[float(v) for v in ne[1:6]], integrator=np.trapz,
+            gamma=g["gamma"].copy(), mu=g["mu"], phi=g["phi"])
+    return np.asarray(sed.value, dtype=np.float64)
+
+
+def cpu_sed_chunked(agnpy, model, g, chunk=25):
+    """one SED on one core, frequency-chunked so the full-grid temporaries stay bounded"""
+    fn = (lambda nn: reference_sed(agnpy, model, g, nn)) if agnpy else (lambda nn: oracle_sed(model, g, nn))
+    return np.concatenate([fn(g["nu"][i:i + chunk]) for i in range(0, N_NU, chunk)])
 
 
 def executed_point_fraction(models, g):
@@ -145,6 +185,82 @@ class ClockSampler:
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+C5_VECTORS = 65536
+
+
+def _max_over_ranks(torch, dist, dev, world, x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_c5(torch, dist, dev, world, group, barrier):
+    """BASELINE configs[4]: 65 536 fit parameter vectors IN TOTAL (Synch + SSC + EC-BLR + EC-DT + the
+    two thermal terms, sherpa-wrapper parameter order and grids, 100 nu), sharded over the ranks, one
+    all-gather, result on the host of every rank.  Strong scaling: the total is fixed."""
+    from agnpy_b200.fit import FitSedBatch
+    from tests import cases
+    pars = cases.c5_parameter_vectors(C5_VECTORS)
+    out = {"vectors_total": C5_VECTORS, "n_gpus": world, "scaling": "strong",
+           "workload": "configs[4]: Synch + SSC + EC-BLR + EC-DT + disk / torus black bodies per fit "
+                       "vector (sherpa-wrapper order, gamma 200 / 300, 100 mu x 50 phi, 100 nu); d_L "
+                       "from z on the host (Planck18, cached)",
+           "points_per_vector": 100 * 200 + 200 * 200 + 100 * 200 * 200 + 100 * 300 * 5000 + 100 * 300 * 50}
+    for integ in ("trapz", "trapz_prefix"):
+        model = FitSedBatch(cases.C5_NU, "BrokenPowerLaw", scenario="ec_blr_dt", integrator=integ,
+                            device=dev, group=group)
+        model(pars[: 512 * world], copy=False)          # warm-up: buffers, scratch, NCCL channel
+        barrier()
+        t0 = time.perf_counter()
+        sed = model(pars, copy=False)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(torch, dist, dev, world, time.perf_counter() - t0)
+        ok = bool(np.isfinite(sed).all() and (sed > 0).any() and sed.shape == (C5_VECTORS, 100))
+        out[integ] = {"seconds": dt, "model_seds_per_s": C5_VECTORS / dt, "finite": ok,
+                      "integrand_gpts_per_s": C5_VECTORS * out["points_per_vector"] / dt / 1e9}
+        del model
+    out["note"] = ("end to end through agnpy_b200.fit.FitSedBatch.__call__: host parameter table in, "
+                   "[65536, 100] SEDs in pinned host memory out on every rank; 'trapz' = the direct "
+                   "per-point kernels, 'trapz_prefix' = the same np.trapz integral with the (mu, phi) "
+                   "sum taken first (DESIGN.md section 4)")
+    return out
+
+
+def bench_c4(torch, dist, dev, world, group, barrier):
+    """BASELINE configs[3]: one EC-BLR SED on 1000 nu x 1000 gamma x 200 mu x 100 phi = 2e10 points,
+    the frequency grid dealt round-robin over the ranks, one all-gather.  Device time per SED
+    (CUDA events around the launches and the collective, max over ranks)."""
+    from agnpy_b200.batch import SedBatch
+    nu = np.logspace(15, 30, 1000)
+    plan = SedBatch("ec_blr", nu, "BrokenPowerLaw", gamma=np.logspace(1, 9, 1000),
+                    mu=np.linspace(-1, 1, 200), phi=np.linspace(0, 2 * np.pi, 100), device=dev,
+                    group=group, shard="nu" if world > 1 else "models")
+    model = synthetic_models(1)
+    for _ in range(3):
+        out = plan.evaluate_device(model)
+    barrier()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        out = plan.evaluate_device(model)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = _max_over_ranks(torch, dist, dev, world, (time.perf_counter() - t0) / reps)
+    ms = _max_over_ranks(torch, dist, dev, world, e0.elapsed_time(e1) / reps)
+    sed = out.cpu().numpy()
+    return {"n_gpus": world, "scaling": "strong", "points_per_sed": 2e10, "ms_per_sed": ms,
+            "wall_ms_per_sed": wall * 1e3, "integrand_gpts_per_s": 2e10 / (ms * 1e-3) / 1e9,
+            "finite": bool(np.isfinite(sed).all() and (sed > 0).sum() > 500),
+            "workload": "configs[3]: EC-BLR, 1000 nu x 1000 gamma x 200 mu x 100 phi, np.trapz, "
+                        "nu dealt round-robin over the ranks + one all-gather",
+            "limits_at_large_n": "per-rank work is 4 launches + 1 all-gather of 1 KB around "
+                                 "~0.1 ms of kernels: launch and collective latency, not FP64"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -234,18 +350,24 @@ def run_cuda(args):
     plan_e2e = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"],
                         phi=g["phi"], device=dev, group=None if world == 1 else dist.group.WORLD)
     for _ in range(3):
-        res = plan_e2e(models)
+        res = plan_e2e(models, copy=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = plan_e2e(models)
+        res = plan_e2e(models, copy=False)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total * args.steps / float(t.item())
+    res = np.array(res[:1])                      # row 0 for the parity spot check below
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- strong-scaling workloads of BASELINE.json, at every N (all ranks take part) ------------
+    group = None if world == 1 else dist.group.WORLD
+    scaling = {"c5_fit_batch": bench_c5(torch, dist, dev, world, group, barrier),
+               "c4_nu_sharded": bench_c4(torch, dist, dev, world, group, barrier)}
 
     if rank != 0:
         if world > 1:
@@ -257,6 +379,10 @@ def run_cuda(args):
     from tests import cases
     chk = oracle_sed(models[0], g, nu=g["nu"][::8])
     dev_rel, zeros_ok = cases.max_rel_dev(res[0][::8], chk)
+    agnpy_ref = reference_module()
+    ref_dev = None
+    if agnpy_ref is not None:       # the same frequencies through the reference's own code
+        ref_dev, _ = cases.max_rel_dev(res[0][::8], reference_sed(agnpy_ref, models[0], g, g["nu"][::8]))
 
     peak = _lib.fp64_peak(300.0)
     _lib.kernel_timing(True)
@@ -274,14 +400,6 @@ def run_cuda(args):
     if folded:
         frac_pts *= ((N_PHI + 1) // 2) / N_PHI
     executed = pts_per_launch * frac_pts * EXEC_FLOPS_PER_POINT / (k_ms * 1e-3) / 1e12
-    traffic = None
-    tfile = ROOT / "profiles" / "ec_main_traffic.json"
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-
     # single-call drop-in latency (the literal reference call with Quantities)
     import agnpy_b200 as ab
     from agnpy_b200 import spectra, u
@@ -346,9 +464,10 @@ def run_cuda(args):
     extra = {
         "ec_blr_trapz_prefix": {
             "value": len(local) / (fast_ms * 1e-3), "unit": UNIT, "ms_per_step": fast_ms,
-            "kernel": "ec_prefix_kernel", "kernel_ms": fast_kms, "parity_max_rel_dev": fast_dev,
-            "note": "opt-in integrator=trapz_prefix: np.trapz over gamma through suffix sums, same "
-                    "integral / grid / masks (DESIGN.md section 4); not the headline"},
+            "kernel": "ec_moment_kernel", "kernel_ms": fast_kms, "parity_max_rel_dev": fast_dev,
+            "note": "opt-in integrator=trapz_prefix: the same np.trapz integral with the (mu, phi) sum "
+                    "taken before the gamma sum (prefix moments of the sorted pair table), same grid "
+                    "and masks (DESIGN.md section 4); not the headline"},
         "ssc_config1": {
             "value": MODELS_PER_GPU / (ssc_ms * 1e-3), "unit": UNIT, "ms_per_step": ssc_ms,
             "workload": "configs[0]: SSC of the tutorial blob, 100 nu x 200 seed nu x 200 gamma, "
@@ -359,16 +478,20 @@ def run_cuda(args):
             "algorithmic_flops_per_point": 24, "parity_max_rel_dev": ssc_dev},
     }
 
-    # CPU baseline: the oracle (reference arithmetic), 1 core, bounded sample
+    extra.update(scaling)
+
+    # CPU baseline: the reference's own code (or the oracle port), 1 core, bounded sample
     t0 = time.perf_counter()
     n_cpu = 0
     while True:
-        _oracle_chunked(models[n_cpu], g)
+        cpu_sed_chunked(agnpy_ref, models[n_cpu], g)
         n_cpu += 1
         if time.perf_counter() - t0 > 12 or n_cpu >= 3:
             break
     cpu_dt = time.perf_counter() - t0
     cpu_value = n_cpu / cpu_dt
+    cpu_kind = "reference (agnpy 0.5.0 from baseline/_ref, CGS-stubbed astropy units)" if agnpy_ref \
+        else "port"
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
@@ -380,36 +503,45 @@ def run_cuda(args):
                          "the path is FP64-pipe bound",
                    "collective": "none" if world == 1 else "one NCCL all_gather_into_tensor of "
                                  f"{MODELS_PER_GPU}x{N_NU} f64 per rank inside the step",
-                   "parity_vs_oracle_max_rel_dev": dev_rel, "parity_zeros_exact": zeros_ok},
+                   "parity_vs_oracle_max_rel_dev": dev_rel, "parity_zeros_exact": zeros_ok,
+                   "parity_vs_reference_max_rel_dev": ref_dev},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(total * 176),
                 "d2h_bytes_per_step": int(total * N_NU * 8),
-                "api": "agnpy_b200.batch.SedBatch.__call__ (host numpy in/out, pinned staging)",
+                "api": "agnpy_b200.batch.SedBatch.__call__(models, copy=False): host numpy in, the "
+                       "gathered [N*256, 200] block in pinned host memory out on every rank",
                 "single_call_us": single_us,
                 "single_call_api": "ExternalCompton.evaluate_sed_flux_blr (Quantity in/out, "
                                    "agnpy_b200_ec_sed_host)"},
         "integrand_gpts_per_s": total * N_NU * N_GAMMA * N_MU * N_PHI / (ms_per_step * 1e-3) / 1e9,
         "roofline": {
-            "bound": "fp64", "kernel": "ec_main_poly_kernel<J=4>", "achieved": achieved,
-            "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
-            "traffic": traffic,
-            "peak_source": "live DFMA-chain microbenchmark agnpy_b200_fp64_peak on this GPU "
-                           "(MEASURED_PEAKS.json has no FP64 entry)",
+            "bound": "fp64", "kernel": "ec_main_poly7_kernel (64 threads x 8 pairs)",
+            "achieved": executed, "peak": peak / 1e12, "unit": "TFLOP/s",
+            "frac": executed / (peak / 1e12), "traffic": None,
+            "what": "EXECUTED FP64 work of the dominant kernel: 2 DFMA (4 flop) per visited integrand "
+                    "point x visited points per launch / CUDA-event time of that launch, over the "
+                    "measured DFMA-chain peak of this GPU",
+            "fp64_flops_per_visited_point": EXEC_FLOPS_PER_POINT,
+            "visited_point_fraction": frac_pts, "phi_axis_folded": folded,
             "kernel_ms": k_ms, "kernel_launches_timed": int(kn),
-            "algorithmic_flops_per_point": FLOPS_PER_POINT,
-            "executed": {"tflops": executed, "frac": executed / (peak / 1e12),
-                         "fp64_flops_per_visited_point": EXEC_FLOPS_PER_POINT,
-                         "visited_point_fraction": frac_pts, "phi_axis_folded": folded},
-            "note": "frac > 1 is expected: the nominal 16 flop/point charges two divisions and the "
-                    "(gamma,nu)/(mu,phi)-only subexpressions per point; the kernel hoists them "
-                    "(2 DFMA per point: wf*K = P + Q b^2 + R b with per-(gamma,nu) tables) and "
-                    "skips points the reference masks to exactly 0; on a mirror-symmetric phi grid "
-                    "(the reference's default) the two points of a mirror pair share one "
-                    "evaluation. 'executed' counts only the DFMAs actually issued."},
-        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{n_cpu} SED(s) of the same workload (oracle = reference numpy "
-                                   "arithmetic, nu-chunked by 25), 1 thread",
+            "kernel_share_of_step": k_ms / ms_per_step,
+            "peak_source": "live DFMA-chain microbenchmark agnpy_b200_fp64_peak on this GPU "
+                           "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 x 64 x 2 x 1.965 GHz "
+                           "= 37.2 TFLOP/s)",
+            "algorithmic": {
+                "flops_per_point": FLOPS_PER_POINT, "tflops": achieved,
+                "over_peak": achieved / (peak / 1e12), "speedup_over_executed": achieved / executed,
+                "note": "SURVEY 8(a) nominal count (16 flop per point of the full 2e8-point grid, two "
+                        "divisions included) over the same time: above peak because the divisions and "
+                        "all (gamma,nu)-only / (mu,phi)-only factors are hoisted into tables (2 DFMA "
+                        "per point: wf K = P + Q b^2 + R b), points the reference masks to exactly 0 "
+                        "are skipped and mirror pairs of the symmetric phi grid share one evaluation"},
+            "traffic_note": "DRAM traffic is not measurable in-run; ncu: profiles/r2*_ec_main_poly7_full.txt "
+                            "(~1.7 % of HBM peak: the path is FP64-pipe bound)"},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": cpu_kind,
+                         "sample": f"{n_cpu} SED(s) of the same workload, nu-chunked by 25, 1 thread "
+                                   "(the reference is single-threaded)",
                          "host_cpus": os.cpu_count()},
         "clocks": clocks,
         "extra": extra,
@@ -420,28 +552,33 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
-def _oracle_chunked(model, g, chunk=25):
-    return np.concatenate([oracle_sed(model, g, nu=g["nu"][i:i + chunk])
-                           for i in range(0, N_NU, chunk)])
+_REF = None
 
 
-# ---------------------------------------------------------------------------------------------
 def _ref_worker(job):
     model_bytes, lo, hi = job
     from agnpy_b200 import _lib
     model = np.frombuffer(model_bytes, dtype=_lib.MODEL_DTYPE)[0]
     g = grids()
+    if _REF is not None:
+        return reference_sed(_REF, model, g, g["nu"][lo:hi])
     return oracle_sed(model, g, nu=g["nu"][lo:hi])
 
 
 def run_reference(args):
-    """CPU arm: the reference cannot be installed here (astropy/matplotlib absent, no network),
-    so this times the oracle port (the reference's numpy arithmetic) on all host cores: one
-    step = one SED of the same workload, its 200 frequencies split over a process pool."""
+    """CPU arm: the reference's own implementation of the path on all host cores.  The reference
+    (agnpy v0.5.0) is installed offline into baseline/_ref (`pip install --no-deps --target`), which
+    travels with the repo; astropy has no wheel, so it runs on the miniature astropy of
+    oracle/astropy_stub (units with astropy's semantics; the reference's own test-suite passes on
+    it).  One step = one SED of the same workload through ExternalCompton.evaluate_sed_flux_blr,
+    its 200 frequencies split over a process pool (the reference itself is single-threaded).  If
+    the install is absent the oracle port of the same numpy arithmetic is timed instead."""
+    global _REF
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    _REF = reference_module()       # imported before the fork: the workers inherit it
     cores = max(1, min(os.cpu_count() or 1, 32))
     chunk = 4
     models = synthetic_models(max(args.steps + args.warmup, 1))
@@ -455,18 +592,23 @@ def run_reference(args):
             pool.map(_ref_worker, jobs_for(models[args.warmup + i:args.warmup + i + 1]))
         dt = time.perf_counter() - t0
     value = args.steps / dt
+    kind = "reference" if _REF is not None else "port"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": "1 SED per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{args.steps} step(s) x 1 SED, nu split in chunks of {chunk} "
                                    f"over {cores} processes",
                          "host_cpus": os.cpu_count(),
-                         "why_port": "agnpy needs astropy+matplotlib, not installable offline; the "
-                                     "oracle restates its numpy arithmetic (oracle/agnpy_oracle.py)"},
+                         "how": ("unmodified agnpy 0.5.0 from baseline/_ref: ExternalCompton."
+                                 "evaluate_sed_flux_blr with Quantities; astropy replaced by "
+                                 "oracle/astropy_stub (CGS-consistent units, no wheel for astropy in this "
+                                 "image)") if _REF is not None else
+                                "reference install absent: oracle port of its numpy arithmetic "
+                                "(oracle/agnpy_oracle.py)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -1,4 +1,8 @@
-"""Development aid: time ec_main variants (AGNPY_B200_EC_PLAN / AGNPY_B200_EC_NU_CHUNK knobs)."""
+"""Development aid: time the EC-BLR np.trapz main kernel under the A/B knobs of ec.cu
+(AGNPY_B200_EC_V6, AGNPY_B200_EC_PLAN="T,J", AGNPY_B200_EC_ACC2, AGNPY_B200_EC_LNU).
+Usage: python scripts/tune_ec.py ["V6=1 PLAN=128,4" "PLAN=64,8 LNU=4" ...]   (default: a built-in sweep)
+Prints, per variant: wall per step and main-kernel time for 256 models, SED/s, and the largest
+deviation from the first variant (all variants must agree to rounding)."""
 import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -9,35 +13,50 @@ from agnpy_b200.batch import SedBatch
 
 torch.cuda.set_device(0)
 g = bench.grids()
+KNOBS = ("V6", "PLAN", "ACC2", "LNU", "NOFOLD")
+
+
 def run(n_models, reps=8):
     models = bench.synthetic_models(n_models)
     plan = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"], phi=g["phi"])
     d_models = torch.from_numpy(np.ascontiguousarray(models).view(np.float64).reshape(n_models, -1).copy()).cuda()
     d_out = torch.empty(n_models, g["nu"].size, dtype=torch.float64, device="cuda")
-    for _ in range(3): plan.launch(d_models, d_out)
+    for _ in range(3):
+        plan.launch(d_models, d_out)
     torch.cuda.synchronize()
     _lib.kernel_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps): plan.launch(d_models, d_out)
-    e1.record(); torch.cuda.synchronize()
-    kms, kn = _lib.kernel_timing_read(); _lib.kernel_timing(False)
+    for _ in range(reps):
+        plan.launch(d_models, d_out)
+    e1.record()
+    torch.cuda.synchronize()
+    kms, kn = _lib.kernel_timing_read()
+    _lib.kernel_timing(False)
     return e0.elapsed_time(e1) / reps, kms / max(kn, 1), d_out.cpu().numpy()
 
+
+variants = sys.argv[1:] or [
+    "V6=1 PLAN=128,4", "PLAN=128,4", "PLAN=128,4 ACC2=1", "PLAN=64,8", "PLAN=64,8 LNU=4", "PLAN=64,8 LNU=8",
+    "PLAN=64,4", "PLAN=64,4 ACC2=1", "PLAN=128,8", "PLAN=64,8 NOFOLD=1", "V6=1 PLAN=128,8 NOFOLD=1",
+]
 ref = None
-variants = [(None, p, sg) for p in (None,) for sg in (None, "4")]
-for v4, plan_s, sg in variants:
-    if True:
-        if v4: os.environ["AGNPY_B200_EC_V4"] = v4
-        else: os.environ.pop("AGNPY_B200_EC_V4", None)
-        if plan_s: os.environ["AGNPY_B200_EC_PLAN"] = plan_s
-        else: os.environ.pop("AGNPY_B200_EC_PLAN", None)
-        if sg: os.environ["AGNPY_B200_EC_LNU"] = sg
-        else: os.environ.pop("AGNPY_B200_EC_LNU", None)
-        res = []
-        for n in (1, 64, 256):
-            ms, kms, out = run(n)
-            if ref is None and n == 64: ref = out
-            if n >= 64: dev = float(np.nanmax(np.abs(out[:64] / np.where(ref != 0, ref, 1) - 1) * (ref != 0)))
-            res.append(f"n={n}: {ms*1e3:8.1f} us (main {kms*1e3:8.1f} us)")
-        print(f"v4={v4} plan={plan_s} sg={sg}: " + " | ".join(res) + f" | dev vs first {dev:.1e}", flush=True)
+for v in variants:
+    for k in KNOBS:
+        os.environ.pop("AGNPY_B200_EC_" + k, None)
+    for item in v.split():
+        k, val = item.split("=")
+        os.environ["AGNPY_B200_EC_" + k] = val
+    try:
+        ms1, k1, _ = run(1)
+        ms, kms, out = run(256)
+    except Exception as exc:  # a variant that does not launch must not stop the sweep
+        print(f"{v:32s} FAILED: {exc}", flush=True)
+        continue
+    if ref is None:
+        ref = out
+    nz = ref != 0
+    dev = float(np.max(np.abs(out[nz] / ref[nz] - 1)))
+    same_zeros = bool(np.array_equal(out == 0, ref == 0))
+    print(f"{v:32s} n=1: {ms1*1e3:7.1f} us (main {k1*1e3:6.1f}) | n=256: {ms:7.3f} ms (main {kms:7.3f} ms) "
+          f"{256 / ms * 1e3:9.0f} SED/s | dev vs first {dev:.1e} zeros {same_zeros}", flush=True)

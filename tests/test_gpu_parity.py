@@ -455,3 +455,36 @@ def test_ssc_energy_loss_rate():
     thomson = ab.Synchrotron(blob).electron_energy_loss_rate(gamma)
     U_B = c["B"] ** 2 / (8 * np.pi)
     np.testing.assert_allclose(thomson.value, 4 / 3 * orc.SIGMA_T * orc.C_LIGHT * U_B * gamma**2, rtol=1e-14)
+
+
+def test_trapz_loglog_callable():
+    """agnpy_b200.trapz_loglog(y, x, axis) as a function (utils/math.py:55-119): the reference's own
+    power-law test (utils/tests/test_utils.py:30-39: exact for power laws, 1 %) and agreement with the
+    oracle's restatement (pinned bit-for-bit to the reference's function) on arrays with zeros, a
+    repeated abscissa, an m = -1 interval and a non-trailing axis; `intervals=True`; units kept."""
+    from oracle import agnpy_oracle as orc
+    x = np.logspace(2, 5, 100)
+    for index in np.arange(-2.0, 2.5, 0.5):
+        for p in (-1.0, 0.0, 1.0):
+            y = 10.0**p * x**index
+            exact = 10.0**p * (np.log(x[-1] / x[0]) if index == -1 else
+                               (x[-1] ** (index + 1) - x[0] ** (index + 1)) / (index + 1))
+            got = ab.trapz_loglog(y, x, axis=0)
+            assert got == pytest.approx(exact, rel=1e-12)
+            assert got == pytest.approx(orc.trapz_loglog(y, x, axis=0), rel=1e-13)
+    rng = np.random.default_rng(3)
+    xg = np.sort(10 ** rng.uniform(0, 6, 40))
+    xg[7] = xg[6]                                   # repeated abscissa: that interval is 0
+    y = 10 ** rng.uniform(-30, 5, (40, 17, 3))
+    y[5:9, 2, :] = 0.0                              # zeros switch their intervals off
+    y[20:22, 4, 1] = (3.0 / xg[20:22])              # m = -1 exactly on one interval
+    for axis, yy in ((0, y), (1, np.moveaxis(y, 0, 1)), (-1, np.moveaxis(y, 0, -1))):
+        want = orc.trapz_loglog(np.moveaxis(yy, axis, 0), xg, axis=0)
+        got = ab.trapz_loglog(yy, xg, axis=axis)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=1e-12)
+    per_interval = ab.trapz_loglog(y, xg, axis=0, intervals=True)
+    assert per_interval.shape == (39, 17, 3) and np.all(per_interval[6] == 0)
+    np.testing.assert_allclose(per_interval.sum(axis=0), ab.trapz_loglog(y, xg, axis=0), rtol=1e-12)
+    q = ab.trapz_loglog(y[:, 0, 0] * u.Unit("erg cm-3"), xg * u.cm, axis=0)
+    assert q.value == pytest.approx(float(ab.trapz_loglog(y[:, 0, 0], xg, axis=0)))
