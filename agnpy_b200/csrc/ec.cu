@@ -19,7 +19,7 @@
 // Map of this file:
 //   ec_tables_kernel / ec_tables2_kernel   gamma table, pair table (sorted by c, optionally with
 //                                          the phi axis folded), {A,G} table, polynomial rows
-//   ec_main_poly_kernel<J>                 np.trapz, >= 512 pairs: 2 DFMA per point (the default)
+//   ec_main_poly_kernel<J,T>               np.trapz, >= 512 pairs: 2 DFMA per point (the default)
 //   ec_main_kernel<INTEG,J>                trapz_loglog, and np.trapz with few pairs (4 instr/pt)
 //   ec_prefix_kernel                       opt-in: np.trapz through suffix sums over gamma
 //   ec_finish_kernel                       fixed-order sum of the warp partials x prefactor
@@ -84,7 +84,7 @@ __device__ __forceinline__ double disk_epsilon(double L_disk, double M_BH, doubl
 // G_k the pair's threshold c falls -- is still taken for each partner separately with the
 // reference's formula whenever c is inside the guard band (ec_main_poly_kernel).
 // ---------------------------------------------------------------------------------------------
-constexpr int kAngCols = 7, kRawCols = 5;
+constexpr int kAngCols = 7, kRawCols = 6;  // raw column 5: sorted 64-bit keys of the segments
 __device__ __forceinline__ void ec_pair_values(
     int variant, const agnpy_model_t& M, const double* __restrict__ mu, int n_mu,
     const double* __restrict__ phi, int n_phi, int imu, int iphi, double& eps, double& omc,
@@ -173,15 +173,30 @@ __device__ __forceinline__ void ec_pairs_role(
 // deterministic order -- exchanged by warp shuffles below stride 32 and through shared memory
 // above.
 constexpr int kPairSeg = 1024;
+// one sorted pair -> its row of the table
+__device__ __forceinline__ void ec_pair_store(const double* __restrict__ raw, int n_pairs,
+                                              double* __restrict__ row, int src, int j) {
+    const double e = raw[src], o = raw[n_pairs + src], w = raw[2 * n_pairs + src];
+    row[j] = e;
+    row[n_pairs + j] = o;
+    row[2 * n_pairs + j] = 1.0 / (e * o);
+    row[3 * n_pairs + j] = w;
+    row[4 * n_pairs + j] = 2.0 * (e * o);
+    row[5 * n_pairs + j] = raw[3 * n_pairs + src];
+    row[6 * n_pairs + j] = raw[4 * n_pairs + src];
+}
+// `keys` == nullptr (one segment): the sorted rows are written directly; else the sorted keys of
+// this segment are stored for ec_pairs_merge_kernel, which interleaves the segments.
 __device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ raw, int n_pairs,
-                                                   double* __restrict__ row, int seg,
+                                                   double* __restrict__ row,
+                                                   unsigned long long* __restrict__ keys, int seg,
                                                    unsigned long long* s_x) {
     const int t = threadIdx.x, j0 = seg * kPairSeg, cnt = min(kPairSeg, n_pairs - j0);
     unsigned long long v = 0ull;  // padding sorts behind every real pair
     if (t < cnt) {
         const double c = 2.0 * (raw[j0 + t] * raw[n_pairs + j0 + t]);
         const unsigned hi = (c > 0.0) ? (unsigned)(__double_as_longlong(c) >> 32) : 0u;
-        v = ((unsigned long long)hi << 32) | (unsigned)(~(unsigned)t);
+        v = ((unsigned long long)hi << 32) | (unsigned)(~(unsigned)(j0 + t));  // unique over the model
     }
     for (int size = 2; size <= kPairSeg; size <<= 1) {
         const bool desc = (t & size) == 0;
@@ -200,16 +215,35 @@ __device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ ra
         }
     }
     if (t < cnt) {
-        const int src = j0 + (int)(~(unsigned)(v & 0xffffffffull)), j = j0 + t;
-        const double e = raw[src], o = raw[n_pairs + src], w = raw[2 * n_pairs + src];
-        row[j] = e;
-        row[n_pairs + j] = o;
-        row[2 * n_pairs + j] = 1.0 / (e * o);
-        row[3 * n_pairs + j] = w;
-        row[4 * n_pairs + j] = 2.0 * (e * o);
-        row[5 * n_pairs + j] = raw[3 * n_pairs + src];
-        row[6 * n_pairs + j] = raw[4 * n_pairs + src];
+        if (keys) keys[j0 + t] = v;
+        else ec_pair_store(raw, n_pairs, row, (int)(~(unsigned)(v & 0xffffffffull)), j0 + t);
     }
+}
+
+// More than one segment: the global position of a sorted key is its position in its own segment
+// plus the number of larger keys in every other segment (keys are unique), found by binary search.
+// A globally sorted table halves the spread of first-unmasked indices inside a warp of the main
+// kernel (a 1024-pair segment covers the whole range of thresholds, 1/n_seg of the table does not).
+__global__ void __launch_bounds__(256) ec_pairs_merge_kernel(const double* __restrict__ raw, int n_pairs,
+                                                             int n_seg, double* __restrict__ ang) {
+    const int m = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pairs) return;
+    const double* r = raw + (size_t)m * kRawCols * n_pairs;
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(r + 5 * (size_t)n_pairs);
+    const unsigned long long key = keys[j];
+    const int own = j / kPairSeg;
+    int rank = j - own * kPairSeg;
+    for (int seg = 0; seg < n_seg; ++seg) {
+        if (seg == own) continue;
+        const int j0 = seg * kPairSeg, cnt = min(kPairSeg, n_pairs - j0);
+        int lo = 0, hi = cnt;  // first position whose key is smaller (descending order)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[j0 + mid] > key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    ec_pair_store(r, n_pairs, ang + (size_t)m * kAngCols * n_pairs, (int)(~(unsigned)(key & 0xffffffffull)), rank);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// np.trapz main path (v6): the integrand as a polynomial in b, frequency-incremental masks.
+// np.trapz main path: the integrand as a polynomial in b, frequency-incremental masks.
 //
 // With the trapz weight folded into wf_k = w_k N_e(gamma_k)/gamma_k^2 the summand of the gamma
 // integral is
@@ -492,19 +526,9 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
 //
 // ec_tables2_kernel writes one row per (nu, model): {Q,R}[n] (16-byte pairs), G[n], SP[n+1]
 // and the index range where y = 1 - eps_s/gamma < 1e-8 (G ill-conditioned).
-// ec_main_poly_kernel: grid = (S pair slices, nu chunks, models), 128 threads x J consecutive
-// pairs (phi fastest, so the first unmasked indices of a warp lie close together).  A block keeps
-// its pairs in registers and walks L_nu consecutive frequencies; the row of frequency i+1 streams
-// into the second shared-memory buffer (cp.async) while frequency i is integrated.  The first
-// unmasked index -- first k with G_k <= c, as in the v4 kernel above -- moves up by a few grid
-// points per frequency step (G_k grows with nu), so after the binary search of the first
-// frequency it is advanced by three probes and verified; anything unexpected (descending nu,
-// coarse grids) falls back to the binary search.  Comparisons run on the bit patterns of the
-// positive doubles (integer pipe, not FP64).  The guard band around c (|hi32(G) - hi32(c)| <= 3,
-// i.e. >= 1.4e-6 relative) and the exact re-decision inside it are those of the v4 kernel.
 // ---------------------------------------------------------------------------------------------
 // row of one (nu, model): {Q,R}[n + kRowPad] (the pad entries are zero: the unrolled gamma loop may run
-// up to 3 steps past the last electron index), G[n], SP[n + 1], {ill_lo, ill_hi}; even word count
+// up to kRowPad - 1 steps past the last electron index), G[n], SP[n + 1], {ill_lo, ill_hi}; even word count
 constexpr int kRowPad = 4;
 __host__ __device__ __forceinline__ int ec_row_words(int n_gamma) {
     return (2 * (n_gamma + kRowPad) + 2 * n_gamma + 2 + 1) & ~1;
@@ -575,8 +599,11 @@ __global__ void __launch_bounds__(kTab2Threads) ec_tables2_kernel(
     __shared__ unsigned long long s_x[kPairSeg];
     const int m = blockIdx.y;
     if ((int)blockIdx.x < n_seg) {
-        ec_pairs_sort_role(raw + (size_t)m * kRawCols * n_pairs, n_pairs, ang + (size_t)m * kAngCols * n_pairs,
-                           blockIdx.x, s_x);
+        const double* r = raw + (size_t)m * kRawCols * n_pairs;
+        // raw column 5 holds the keys; const_cast: it is scratch of this launch sequence
+        unsigned long long* keys = n_seg > 1
+            ? reinterpret_cast<unsigned long long*>(const_cast<double*>(r) + 5 * (size_t)n_pairs) : nullptr;
+        ec_pairs_sort_role(r, n_pairs, ang + (size_t)m * kAngCols * n_pairs, keys, blockIdx.x, s_x);
     } else {
         ec_poly_row_role(models, nu, n_nu, gamma, n_gamma, gt, hull, rows,
                          ((int)blockIdx.x - n_seg) * (kTab2Threads / 32) + (threadIdx.x >> 5), m);
@@ -616,21 +643,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
 }
 
-// first k with G_k <= c on the bit patterns (G descending; +inf for gamma <= eps_s)
-__device__ __forceinline__ int ec_search_first_le(const long long* s_Gi, int n_gamma, long long c) {
-    int lo = 0, hi = n_gamma;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (s_Gi[mid] <= c) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-// move a first-(G_k <= c) index found for a neighbouring frequency to the current table
-__device__ __forceinline__ int ec_search_step(const long long* s_Gi, int n_gamma, long long c, int k) {
-    while (k < n_gamma && s_Gi[k] > c) ++k;
-    while (k > 0 && s_Gi[k - 1] <= c) --k;
-    return k;
-}
 // the reference's own decision (kernels.py:36-40) for one (nu, pair)
 __device__ __noinline__ int ec_first_unmasked_ref(const double* __restrict__ gm, int n_gamma,
                                                   const double* __restrict__ a_eps,
@@ -649,214 +661,37 @@ __device__ __forceinline__ long long warp_min_ll(long long v) {
     return v;
 }
 
-template <int J>
-__global__ void __launch_bounds__(128, 4) ec_main_poly_kernel(
-    const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
-    const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma,
-    const double* __restrict__ rows, const double* __restrict__ ang, int n_pairs, int S, int L_nu,
-    double* __restrict__ part) {
-    extern __shared__ __align__(16) double sh[];  // L_nu rows, then L_nu mbarriers
-    const int slice = blockIdx.x, m = blockIdx.z;
-    const int i0 = blockIdx.y * L_nu, i1 = min(i0 + L_nu, n_nu);
-    const int T = blockDim.x, tid = threadIdx.x, W_per_block = T >> 5;
-    const int row_words = ec_row_words(n_gamma);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + (size_t)L_nu * row_words);
-    if (tid == 0) {
-        for (int r = 0; r < i1 - i0; ++r) mbar_init(bars + r, 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    const double* g_gm = gt + (size_t)m * 5 * n_gamma;
-    const double* a_eps = ang + (size_t)m * kAngCols * n_pairs;
-    const double* a_omc = a_eps + n_pairs;
-    const double* a_b = a_omc + n_pairs;
-    const double* a_W = a_b + n_pairs;
-    const double* a_c = a_W + n_pairs;
-    const double* a_omc_p = a_c + n_pairs;  // mirror partner of a folded pair (W_p = 0: none)
-    const double* a_W_p = a_omc_p + n_pairs;
-    const int klo = hull[2 * m], khi = hull[2 * m + 1];  // non-zero range of n_e
-    const double* g_rows = rows + (size_t)m * n_nu * row_words;
-    const int jbase = (slice * T + tid) * J;
-    if (tid == 0) {  // all rows of this block's frequency chunk, one bulk copy each
-        const unsigned row_bytes = (unsigned)row_words * sizeof(double);
-        for (int r = 0; r < i1 - i0; ++r) {
-            mbar_expect_tx(bars + r, row_bytes);
-            bulk_copy_g2s(sh + (size_t)r * row_words, g_rows + (size_t)(i0 + r) * row_words, row_bytes,
-                          bars + r);
-        }
-    }
-
-    double b[J], b2[J];
-    int hc[J];  // high word of c (> 0); -1 marks a pair that never contributes
-    long long cmax = -1, cmin = LLONG_MAX;  // bits of c over the live pairs of the warp
-#pragma unroll
-    for (int jj = 0; jj < J; ++jj) {
-        const int j = jbase + jj;
-        const bool valid = j < n_pairs;
-        b[jj] = valid ? a_b[j] : 0.0;
-        b2[jj] = b[jj] * b[jj];
-        const double c = valid ? a_c[j] : -1.0;
-        const long long ci = (c > 0.0) ? __double_as_longlong(c) : -1LL;
-        hc[jj] = (int)(ci >> 32);
-        if (ci > 0) { cmax = max(cmax, ci); cmin = min(cmin, ci); }
-    }
-    cmax = warp_max_ll(cmax);
-    cmin = warp_min_ll(cmin);
-    const bool warp_live = cmax > 0 && khi >= 0;
-    int wlo = 0, whi = 0;  // first k with G_k <= cmax / <= cmin for the current frequency
-    for (int i = i0; i < i1; ++i) {
-        // warps run through the chunk independently: the only wait is for row i to have landed
-        mbar_wait(bars + (i - i0), 0);
-        const double* s_row = sh + (size_t)(i - i0) * row_words;
-        const double2* s_QR = reinterpret_cast<const double2*>(s_row);
-        const long long* s_Gi = reinterpret_cast<const long long*>(s_row + 2 * (n_gamma + kRowPad));
-        const int* s_Gh = reinterpret_cast<const int*>(s_Gi);  // [2k+1] = high word
-        const double* s_SP = s_row + 2 * (n_gamma + kRowPad) + n_gamma;
-        double thread_sum = 0.0;
-        if (warp_live) {
-            // warp-uniform index window [wlo, whi]: every live pair's first unmasked index lies in it
-            if (i == i0) {
-                wlo = ec_search_first_le(s_Gi, n_gamma, cmax);
-                whi = ec_search_first_le(s_Gi, n_gamma, cmin);
-            } else {
-                wlo = ec_search_step(s_Gi, n_gamma, cmax, wlo);
-                whi = ec_search_step(s_Gi, n_gamma, cmin, whi);
-            }
-            // per pair: lo = wlo + #{k in [wlo, whi) : G_k > c}   (G descending: a prefix count).
-            // The count compares high words only; a tie there lands inside the guard band below
-            // and is re-decided exactly.
-            int lo[J];
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj) lo[jj] = wlo;
-            for (int k = wlo; k < whi; ++k) {
-                const int gh = s_Gh[2 * k + 1];
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) lo[jj] += (gh > hc[jj]) ? 1 : 0;
-            }
-            // guard band: a neighbour of the index within ~1e-6 of c, an ill-conditioned G in the
-            // window, or a non-finite c -> decide that pair with the reference's own formula
-            const int2 ill = *reinterpret_cast<const int2*>(s_SP + n_gamma + 1);
-            const bool w_ill = max(wlo - 1, 0) < ill.y && min(whi, n_gamma - 1) >= ill.x;
-            unsigned doubt = 0;
-            int tmin = INT_MAX, tmax = 0;  // over this thread's live pairs
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj) {
-                const int k = lo[jj];
-                const int ha = s_Gh[2 * min(k, n_gamma - 1) + 1], hb = s_Gh[2 * max(k - 1, 0) + 1];
-                const bool d = (k < n_gamma && abs(ha - hc[jj]) <= 3) || (k > 0 && abs(hb - hc[jj]) <= 3) ||
-                               w_ill || hc[jj] >= 0x7ff00000;
-                if (hc[jj] >= 0) {
-                    if (d) doubt |= 1u << jj;
-                    tmin = min(tmin, k);
-                    tmax = max(tmax, k);
-                } else {
-                    lo[jj] = n_gamma;
-                }
-            }
-            double fold_corr = 0.0;  // see below; almost always 0
-            if (doubt) {  // rare
-                tmin = INT_MAX;
-                tmax = 0;
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) {
-                    if (doubt & (1u << jj)) {
-                        const int j = jbase + jj;
-                        lo[jj] = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc, j, nu[i], models[m].z);
-                        // folded pair: the mirror partner takes its own decision.  If it starts
-                        // at another index, the shared evaluation (weight W + W_p from lo) is off
-                        // by W_p times the integrand steps between the two indices.
-                        const double W_p = a_W_p[j];
-                        if (W_p != 0.0) {
-                            const int lo_p = ec_first_unmasked_ref(g_gm, n_gamma, a_eps, a_omc_p, j, nu[i],
-                                                                   models[m].z);
-                            const int ka = max(min(lo[jj], lo_p), klo), kb = min(max(lo[jj], lo_p), khi + 1);
-                            double d = 0.0;
-                            for (int k = ka; k < kb; ++k) {
-                                const double2 qr = s_QR[k];
-                                d += (s_SP[k] - s_SP[k + 1]) + fma(qr.y, b[jj], qr.x * b2[jj]);
-                            }
-                            fold_corr += (lo_p < lo[jj]) ? W_p * d : -(W_p * d);
-                        }
-                    }
-                    if (hc[jj] >= 0) { tmin = min(tmin, lo[jj]); tmax = max(tmax, lo[jj]); }
-                }
-            }
-            double acc[J];
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj) acc[jj] = 0.0;
-            const int kbeg = max(__reduce_min_sync(0xffffffffu, tmin), klo);
-            const int kmid = min(max(__reduce_max_sync(0xffffffffu, tmax), kbeg), khi + 1);
-            // phase 1 (a few steps: the pairs of a warp are neighbours in c): lanes join as the
-            // loop passes their first unmasked index
-            for (int k = kbeg; k < kmid; ++k) {
-                const double2 qr = s_QR[k];
-                if (k >= tmax) {
-#pragma unroll
-                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.x, b2[jj], acc[jj]);
-#pragma unroll
-                    for (int jj = 0; jj < J; ++jj) acc[jj] = fma(qr.y, b[jj], acc[jj]);
-                } else if (k >= tmin) {
-#pragma unroll
-                    for (int jj = 0; jj < J; ++jj)
-                        if (k >= lo[jj]) acc[jj] = fma(qr.y, b[jj], fma(qr.x, b2[jj], acc[jj]));
-                }
-            }
-            // phase 2: every live lane is above its gamma_min -> 2 DFMA per integrand point
-            // four gamma steps per trip and no remainder loop: the row carries kRowPad zero entries
-            // after the last index, so running past khi adds exact zeros
-            for (int k = kmid; k <= khi; k += 4) {
-                const double2 q0 = s_QR[k], q1 = s_QR[k + 1], q2 = s_QR[k + 2], q3 = s_QR[k + 3];
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q0.x, b2[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q0.y, b[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q1.x, b2[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q1.y, b[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q2.x, b2[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q2.y, b[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q3.x, b2[jj], acc[jj]);
-#pragma unroll
-                for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q3.y, b[jj], acc[jj]);
-            }
-#pragma unroll
-            for (int jj = 0; jj < J; ++jj) {
-                const int ks = max(lo[jj], klo);
-                if (ks <= khi) thread_sum = fma(a_W[jbase + jj], acc[jj] + s_SP[ks], thread_sum);
-            }
-            thread_sum += fold_corr;
-        }
-        thread_sum = warp_sum(thread_sum);
-        if ((tid & 31) == 0)
-            part[(((size_t)m * n_nu + i) * S + slice) * W_per_block + (tid >> 5)] = thread_sum;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// np.trapz main path, v7: the same integrand, tables, masks and guard band as ec_main_poly_kernel,
-// with the work *around* the gamma loop restructured.  ncu on v6 (profiles/r1f_ec_main_poly_full.txt,
-// per (warp, nu) unit): 800 DFMA (1600 FP64-pipe cycles) but 2930 cycles of SMSP time; 545 of the
-// 740 other instructions sit outside the loop and collect 48 % of the stall samples -- serial
-// shared-memory probes of the window search (all 32 lanes walking the same entries), two loads and
-// a dozen ALU operations per pair for the guard band, a 5-step shuffle reduction per frequency, and
-// global loads of the pair weights.  A non-FP64 instruction costs the sub-partition a dispatch
-// slot the DFMA stream cannot use (scripts/micro/fp64_mix.cu), so each one removed is worth its
-// share of the run time.  Here:
-//   * window search by lane-parallel probes: lane l tests entry k0 + l, one ballot gives the index
-//     (two independent loads per frequency instead of >= 4 dependent ones; the first frequency of a
-//     chunk uses a 32-way search, 2 round trips at 200 gammas);
-//   * one loop over the window entries [wlo-1, whi] does both the per-pair index count and the
-//     guard-band test (no per-pair loads);
-//   * pair weights live in registers; dead pairs carry W = b = 0 and need no special casing;
-//   * the (mu, phi) partial sums of the L frequencies of a chunk are parked in shared memory and
-//     reduced once per block (8 values per lane + 2 shuffles) instead of once per frequency;
-//   * J = 8 pairs per thread at 64 threads per block keep the 512-pair slices of the folded table
-//     (2500 pairs -> 5 slices) while halving the number of (warp, nu) units; ACC2 gives each pair
-//     two accumulator chains where J = 4 leaves the 8-cycle DFMA latency exposed.
+// ec_main_poly_kernel<J, T>: grid = (S pair slices, nu chunks, models), T threads x J consecutive pairs
+// of the globally c-sorted table (so the first unmasked indices of a warp lie within a few entries
+// of each other).  A block keeps its pairs in registers and walks the L_nu <= 8 frequencies of its
+// chunk; their rows arrive by TMA bulk copies (cp.async.bulk + one mbarrier per row) and the warps
+// run through the chunk independently, no block barrier after the prologue.  Per (warp, nu):
+//   * index window [wlo, whi] = first entries with G_k <= the warp's largest / smallest threshold,
+//     by lane-parallel probes: lane l tests entry k_prev - 1 + l of the new row, one ballot gives the
+//     index (G_k grows with nu, the indices move up by an entry or two per frequency step); the
+//     first frequency of a chunk uses a 32-way search (2 round trips at 200 gammas).  Comparisons run
+//     on the bit patterns of the positive doubles (integer pipe, not FP64);
+//   * one pass over the entries [wlo-1, whi]: per pair the index count lo = wlo + #{G_k > c} (sign
+//     bit of a high-word difference) and the guard band (running unsigned minimum of the same
+//     difference): an entry within 3 units of the high word of c (>= 1.4e-6 relative) next to the
+//     index, an ill-conditioned G in the window or a non-finite c -> that pair is decided with the
+//     reference's own formula (kernels.py:36-40), mirror partners of a folded phi axis separately;
+//   * phase 1 (the ragged start, window-many steps, predicated), phase 2 (2 DFMA per point, 4 gamma
+//     steps per trip, zero-padded rows instead of a remainder loop), then W_j (acc_j + SP[lo_j]);
+//     pair weights live in registers, dead pairs carry W = b = 0 and need no special casing;
+//   * the partial sums of the chunk's frequencies are parked in shared memory and reduced once per
+//     block (8 values per lane + 2 shuffles) instead of once per frequency.
+// Why it looks like this (ncu, profiles/r1f_* -> r2*_ec_main_poly_full.txt): a non-FP64 instruction
+// costs the sub-partition a dispatch slot the DFMA stream cannot use (scripts/micro/fp64_mix.cu), and
+// round 1 executed 1500 instructions per (warp, nu) for 800 DFMAs, 545 of them outside the gamma
+// loop with 48 % of the stall samples.  Now: 1320 instructions for 784 DFMAs (global sort of the
+// pair table: windows of ~2 instead of ~5 entries, 11 instead of 39 wasted DFMAs in the ragged
+// start), 96 registers -> 5 blocks per SM; FP64 pipe 57 % -> 66 % active.  Tried and measured slower
+// (profiles/r2_tune_ec.txt): 8 pairs per thread (64 x 8 ties, 128 x 8 loses: wider windows), a
+// second accumulator chain per pair, 8 gamma steps per trip, and a ring of row buffers with
+// full / empty mbarriers feeding 25-200 frequencies per block (the prologue it amortises is
+// latency other blocks already hide; uneven chunks cost more).
 // ---------------------------------------------------------------------------------------------
 // first k in [0, n] with G_k <= c (G descending), all lanes cooperating: 32 probes per round
 __device__ __forceinline__ int ec_warp_first_le(const long long* __restrict__ s_Gi, int n, long long c,
@@ -887,8 +722,8 @@ __device__ __forceinline__ int ec_warp_step_le(const long long* __restrict__ s_G
     return ec_warp_first_le(s_Gi, n, c, lane);
 }
 
-template <int J, int T, bool ACC2, int MINB>
-__global__ void __launch_bounds__(T, MINB) ec_main_poly7_kernel(
+template <int J, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
     const double* __restrict__ gt, const int* __restrict__ hull, int n_gamma,
     const double* __restrict__ rows, const double* __restrict__ ang, int n_pairs, int S, int L_nu,
@@ -974,22 +809,32 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly7_kernel(
             // the guard band itself: an entry within 3 units of the high word of c (>= 1.4e-6
             // relative) next to the index -> decide that pair with the reference's own formula
             int lo[J];
+            unsigned near[J];  // min over the entries of (high word of c) - (high word of G_k) + 3, unsigned
             unsigned doubt = always_doubt;
 #pragma unroll
-            for (int jj = 0; jj < J; ++jj) lo[jj] = wlo;
-            {
-                const int ka = max(wlo - 1, 0), kb = min(whi, n_gamma - 1);
-                for (int k = ka; k <= kb; ++k) {
-                    const int gh = s_Gh[2 * k + 1];
-                    const int inside = (k >= wlo && k < whi) ? 1 : 0;
+            for (int jj = 0; jj < J; ++jj) { lo[jj] = wlo; near[jj] = 0xffffffffu; }
+            if (wlo >= 1) {  // the entry below the window: guard band only
+                const unsigned gh = (unsigned)s_Gh[2 * (wlo - 1) + 1];
 #pragma unroll
-                    for (int jj = 0; jj < J; ++jj) {
-                        const int d = gh - hc[jj];
-                        lo[jj] += (d > 0) ? inside : 0;
-                        if ((unsigned)(d + 3) <= 6u) doubt |= 1u << jj;
-                    }
+                for (int jj = 0; jj < J; ++jj) near[jj] = min(near[jj], (unsigned)hc[jj] - gh + 3u);
+            }
+            for (int k = wlo; k < whi; ++k) {  // inside: count (sign bit of the difference) and band
+                const unsigned gh = (unsigned)s_Gh[2 * k + 1];
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    const unsigned e = (unsigned)hc[jj] - gh;  // negative: G_k > c, still masked
+                    lo[jj] += (int)(e >> 31);
+                    near[jj] = min(near[jj], e + 3u);
                 }
             }
+            if (whi < n_gamma) {  // the entry at the upper end: guard band only
+                const unsigned gh = (unsigned)s_Gh[2 * whi + 1];
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) near[jj] = min(near[jj], (unsigned)hc[jj] - gh + 3u);
+            }
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj)
+                if (near[jj] <= 6u) doubt |= 1u << jj;
             const int2 ill = *reinterpret_cast<const int2*>(s_SP + n_gamma + 1);
             if (max(wlo - 1, 0) < ill.y && min(whi, n_gamma - 1) >= ill.x) {  // ill-conditioned G in the window
 #pragma unroll
@@ -1028,13 +873,9 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly7_kernel(
             }
             kbeg = max(kbeg, klo);
             kmid = min(max(kmid, kbeg), khi + 1);
-            double acc[J], acc_r[ACC2 ? J : 1];
+            double acc[J];
 #pragma unroll
             for (int jj = 0; jj < J; ++jj) acc[jj] = 0.0;
-            if (ACC2) {
-#pragma unroll
-                for (int jj = 0; jj < (ACC2 ? J : 1); ++jj) acc_r[jj] = 0.0;
-            }
             // phase 1 (a few steps: the pairs of a warp are neighbours in c): lanes join as the
             // loop passes their first unmasked index
             for (int k = kbeg; k < kmid; ++k) {
@@ -1048,14 +889,9 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly7_kernel(
             // after the last index, so running past khi adds exact zeros
             for (int k = kmid; k <= khi; k += 4) {
                 const double2 q0 = s_QR[k], q1 = s_QR[k + 1], q2 = s_QR[k + 2], q3 = s_QR[k + 3];
-#define EC_STEP(q)                                                                       \
+#define EC_STEP(q)                                                                        \
     _Pragma("unroll") for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q.x, b2[jj], acc[jj]); \
-    if (ACC2) {                                                                           \
-        _Pragma("unroll") for (int jj = 0; jj < J; ++jj)                                  \
-            acc_r[ACC2 ? jj : 0] = fma(q.y, b[jj], acc_r[ACC2 ? jj : 0]);                 \
-    } else {                                                                              \
-        _Pragma("unroll") for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q.y, b[jj], acc[jj]); \
-    }
+    _Pragma("unroll") for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q.y, b[jj], acc[jj]);
                 EC_STEP(q0) EC_STEP(q1) EC_STEP(q2) EC_STEP(q3)
 #undef EC_STEP
             }
@@ -1063,8 +899,7 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly7_kernel(
             // exactly 0 past the last electron index); dead pairs have W = 0
 #pragma unroll
             for (int jj = 0; jj < J; ++jj) {
-                const double a = ACC2 ? acc[jj] + acc_r[ACC2 ? jj : 0] : acc[jj];
-                thread_sum = fma(W[jj], a + s_SP[min(max(lo[jj], klo), n_gamma)], thread_sum);
+                thread_sum = fma(W[jj], acc[jj] + s_SP[min(max(lo[jj], klo), n_gamma)], thread_sum);
             }
             thread_sum += fold_corr;
         }
@@ -1318,10 +1153,11 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
     p.J = 1;
     if (integ == AGNPY_INTEG_TRAPZ) {
         p.J = p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
-        // polynomial kernel (>= 512 pairs): 64 threads x 8 consecutive sorted pairs = 512-pair slices
-        // (2500 folded pairs at the default grids -> 5 slices, 2 % padding), measured fastest on B200
-        // (scripts/tune_ec.py, profiles/r2*_tune_ec.txt)
-        if (p.n_pairs >= 512) { p.T = 64; p.J = 8; }
+        // polynomial kernel (>= 512 pairs): 128 threads x 4 consecutive sorted pairs = 512-pair slices
+        // (2500 folded pairs at the default grids -> 5 slices, 2 % padding), 5 blocks per SM at 96
+        // registers: measured fastest on B200 (scripts/tune_ec.py, profiles/r2*_tune_ec.txt); 8 pairs
+        // per thread widen a warp's index window and lose more in the ragged start than they save
+        if (p.n_pairs >= 512) { p.T = 128; p.J = 4; }
     }
     if (const char* e = getenv("AGNPY_B200_EC_PLAN")) {  // development knob: "T,J"
         int t = 0, j = 0;
@@ -1411,6 +1247,11 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         ec_tables2_kernel<<<grid2, kTab2Threads, 0, stream>>>(raw, p.n_pairs, n_seg, ang, models, nu,
                                                               n_nu, gamma, n_gamma, gt, hull, rows);
         note_launch();
+        if (n_seg > 1) {  // interleave the sorted segments into one globally sorted table
+            dim3 grid3((p.n_pairs + 255) / 256, n_models);
+            ec_pairs_merge_kernel<<<grid3, 256, 0, stream>>>(raw, p.n_pairs, n_seg, ang);
+            note_launch();
+        }
     }
     if (prefix) {
         // prefix moments over the sorted segments (the `rows` area is free on this path), then one
@@ -1466,23 +1307,22 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     while ((1 << iters) < n_gamma + 1) ++iters;
     if (v5) {
         const int row_words = ec_row_words(n_gamma);
-        // frequencies per block: as many as keep >= 8 waves of blocks in flight, at most 16
-        int L_nu = 16;
+        // frequencies per block: as many as keep >= 8 waves of blocks in flight, at most 8
+        int L_nu = 8;
         while (L_nu > 1 && (long long)p.S * ((n_nu + L_nu - 1) / L_nu) * n_models < 8LL * 5 * sms) L_nu >>= 1;
         if (const char* e = getenv("AGNPY_B200_EC_LNU")) {  // development knob
             int v = atoi(e);
             if (v >= 1) L_nu = v;
         }
         const size_t row_bytes = (size_t)row_words * sizeof(double);
-        const bool v6 = getenv("AGNPY_B200_EC_V6") != nullptr;  // A/B knob: the round-1 kernel
-        const bool acc2 = getenv("AGNPY_B200_EC_ACC2") != nullptr;
-        // shared memory per block: rows (+ parked partial sums and barriers); keep >= 4 blocks per SM
-        const size_t per_nu = row_bytes + 8 + (v6 ? 0 : (size_t)(p.T + 1) * sizeof(double));
-        // (4 blocks of 128 threads, 6 of 64 threads x 8 pairs, 8 of 64 x 4: the register-limited counts)
-        const int blocks_per_sm = getenv("AGNPY_B200_EC_MINB5") ? 5 : (v6 || p.T >= 128) ? 4 : (p.J == 8 ? 6 : 8);
+        // shared memory per frequency: the row, its parked partial sums and its barrier; blocks per SM
+        // as the register budget allows (5 x 128 threads at 96 registers, 3 at 8 pairs per thread; 6 of
+        // 64 threads x 8 pairs, 8 of 64 x 4)
+        const size_t per_nu = row_bytes + 8 + (size_t)(p.T + 1) * sizeof(double);
+        const int blocks_per_sm = p.T >= 128 ? (p.J == 8 ? 3 : 5) : (p.J == 8 ? 6 : 8);
         const size_t smem_cap = (size_t)(227 * 1024) / blocks_per_sm - 1024;
-        if (v6) { while (L_nu > 1 && L_nu * per_nu > smem_cap) L_nu >>= 1; }
-        else if (L_nu * per_nu > smem_cap) L_nu = (int)std::max<size_t>(1, smem_cap / per_nu);
+        if (L_nu * per_nu > smem_cap) L_nu = (int)std::max<size_t>(1, smem_cap / per_nu);
+        L_nu = std::min(L_nu, 8);
         dim3 grid(p.S, (n_nu + L_nu - 1) / L_nu, n_models);
         const size_t smem6 = L_nu * per_nu;
         timing_begin(stream);
@@ -1493,25 +1333,11 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         KERNEL<<<grid, p.T, smem6, stream>>>(models, nu, n_nu, gt, hull, n_gamma, rows, ang,        \
                                              p.n_pairs, p.S, L_nu, part);                           \
     } while (0)
-        if (v6 && p.T == 128) {
-            if (p.J == 8) EC_LAUNCH_K(ec_main_poly_kernel<8>);
-            else if (p.J == 4) EC_LAUNCH_K(ec_main_poly_kernel<4>);
-            else if (p.J == 2) EC_LAUNCH_K(ec_main_poly_kernel<2>);
-            else EC_LAUNCH_K(ec_main_poly_kernel<1>);
-        } else if (p.T == 64 && p.J == 8) {
-            EC_LAUNCH_K((ec_main_poly7_kernel<8, 64, false, 6>));
-        } else if (p.T == 64 && p.J == 4) {
-            if (acc2) EC_LAUNCH_K((ec_main_poly7_kernel<4, 64, true, 8>));
-            else EC_LAUNCH_K((ec_main_poly7_kernel<4, 64, false, 8>));
-        } else if (p.T == 128 && p.J == 8) {
-            EC_LAUNCH_K((ec_main_poly7_kernel<8, 128, false, 3>));
-        } else if (p.T == 128 && p.J == 4) {
-            if (acc2) EC_LAUNCH_K((ec_main_poly7_kernel<4, 128, true, 4>));
-            else if (getenv("AGNPY_B200_EC_MINB5")) EC_LAUNCH_K((ec_main_poly7_kernel<4, 128, false, 5>));
-            else EC_LAUNCH_K((ec_main_poly7_kernel<4, 128, false, 4>));
-        } else {
-            return fail(AGNPY_ERR_ARG, "ec_sed: unsupported AGNPY_B200_EC_PLAN for the polynomial kernel");
-        }
+        if (p.T == 128 && p.J == 4) EC_LAUNCH_K((ec_main_poly_kernel<4, 128, 5>));
+        else if (p.T == 64 && p.J == 8) EC_LAUNCH_K((ec_main_poly_kernel<8, 64, 6>));
+        else if (p.T == 64 && p.J == 4) EC_LAUNCH_K((ec_main_poly_kernel<4, 64, 8>));
+        else if (p.T == 128 && p.J == 8) EC_LAUNCH_K((ec_main_poly_kernel<8, 128, 3>));
+        else return fail(AGNPY_ERR_ARG, "ec_sed: unsupported AGNPY_B200_EC_PLAN for the polynomial kernel");
 #undef EC_LAUNCH_K
         timing_end(stream);
         note_launch();

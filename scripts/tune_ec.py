@@ -1,5 +1,6 @@
 """Development aid: time the EC-BLR np.trapz main kernel under the A/B knobs of ec.cu
-(AGNPY_B200_EC_V6, AGNPY_B200_EC_PLAN="T,J", AGNPY_B200_EC_ACC2, AGNPY_B200_EC_LNU).
+(AGNPY_B200_EC_PLAN="T,J", AGNPY_B200_EC_LNU, AGNPY_B200_EC_NOFOLD; earlier sweeps, with knobs that
+have since been removed, are kept in profiles/r2_tune_ec.txt).
 Usage: python scripts/tune_ec.py ["V6=1 PLAN=128,4" "PLAN=64,8 LNU=4" ...]   (default: a built-in sweep)
 Prints, per variant: wall per step and main-kernel time for 256 models, SED/s, and the largest
 deviation from the first variant (all variants must agree to rounding)."""
@@ -13,7 +14,7 @@ from agnpy_b200.batch import SedBatch
 
 torch.cuda.set_device(0)
 g = bench.grids()
-KNOBS = ("V6", "PLAN", "ACC2", "LNU", "NOFOLD")
+KNOBS = ("PLAN", "LNU", "NOFOLD")
 
 
 def run(n_models, reps=8):
@@ -36,10 +37,7 @@ def run(n_models, reps=8):
     return e0.elapsed_time(e1) / reps, kms / max(kn, 1), d_out.cpu().numpy()
 
 
-variants = sys.argv[1:] or [
-    "V6=1 PLAN=128,4", "PLAN=128,4", "PLAN=128,4 ACC2=1", "PLAN=64,8", "PLAN=64,8 LNU=4", "PLAN=64,8 LNU=8",
-    "PLAN=64,4", "PLAN=64,4 ACC2=1", "PLAN=128,8", "PLAN=64,8 NOFOLD=1", "V6=1 PLAN=128,8 NOFOLD=1",
-]
+variants = sys.argv[1:] or ["PLAN=128,4", "PLAN=64,8", "PLAN=64,4", "PLAN=128,8", "PLAN=128,4 LNU=4", "PLAN=128,4 NOFOLD=1"]
 ref = None
 for v in variants:
     for k in KNOBS:
