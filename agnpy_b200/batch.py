@@ -175,7 +175,12 @@ class SedBatch:
         self.phi = dev(grids.phi_to_integrate if phi is None else grids.as_grid(phi, "phi"))
         if process in _EC:  # mirror-symmetric phi grid: the EC kernels may fold it
             self.integ |= grids.phi_fold_flag(grids.phi_to_integrate if phi is None else phi)
-        self.nu_seed = dev(grids.nu_to_integrate if nu_seed is None else nu_seed)
+        # the np.trapz SSC kernel locates each electron's seed band by a monotone search: the seed
+        # grid must be strictly ascending (and positive), like every other grid
+        nu_seed = grids.nu_to_integrate if nu_seed is None else grids.as_grid(nu_seed, "nu_seed")
+        if not nu_seed[0] > 0:
+            raise ValueError("nu_seed: frequencies must be positive")
+        self.nu_seed = dev(nu_seed)
         # normalisation grid of the thermal disk SED (targets/targets.py:151, 393-415)
         self.nu_bb_norm = dev(grids.nu_to_integrate_targets)
         self.l_unit = dev(np.logspace(-5, 5, int(l_size)) if process in _TAU_OFF_AXIS

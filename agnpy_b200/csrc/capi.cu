@@ -119,6 +119,9 @@ int agnpy_b200_ssc_sed(int n_models, const agnpy_model_t* models, int ne_kind,
         return fail(AGNPY_ERR_ARG, "ssc_sed: bad sizes or null pointer");
     if (bad_kind(ne_kind) || bad_integ(integ)) return fail(AGNPY_ERR_ARG, "ssc_sed: bad ne_kind/integ");
     if (n_nu > 65535 || n_seed > 65535) return fail(AGNPY_ERR_ARG, "ssc_sed: n_nu/n_seed > 65535");
+    // nu_seed must be strictly ascending and positive (the np.trapz kernel searches it as a monotone
+    // grid); device memory cannot be inspected here cheaply, the host flavour and the Python callers
+    // validate it (agnpy_b200_ssc_sed_host, agnpy_b200.grids.as_grid)
     if (ne_kind == AGNPY_NE_TABLE && (!ne_table || (ssa && !ssa_table)))
         return fail(AGNPY_ERR_ARG, "ssc_sed: AGNPY_NE_TABLE needs n_e (and SSA) tables");
     integ = plain_integ(integ);
@@ -497,6 +500,9 @@ int agnpy_b200_ssc_sed_host(int n_models, const agnpy_model_t* models, int ne_ki
                             const double* gamma, int n_gamma, const double* ne_table,
                             const double* ssa_table, int ssa, int integ, double* sed) {
     if (int rc = need_device()) return rc;
+    for (int j = 1; nu_seed && j < n_seed; ++j)
+        if (!(nu_seed[j] > nu_seed[j - 1]) || !(nu_seed[0] > 0.0))
+            return fail(AGNPY_ERR_ARG, "ssc_sed_host: nu_seed must be strictly ascending and positive");
     if (n_models < 1 || n_nu < 1 || n_gamma < 2 || n_seed < 2 || !models || !nu || !nu_seed ||
         !gamma || !sed)
         return fail(AGNPY_ERR_ARG, "ssc_sed_host: bad sizes or null pointer");

@@ -368,6 +368,42 @@ __device__ __noinline__ int first_unmasked_exact(const double* __restrict__ gm, 
     return lo;
 }
 
+// trapz_loglog over gamma for one pair (utils/math.py:55-119), from its first unmasked index ks:
+// y_k = f_k K_k(b), z_k = gamma_k y_k, carried sequentially.  An interval takes the logarithm-free
+// form of common.cuh (loglog_interval_z); where neighbouring samples differ by more than a factor
+// 2.1, or a sample is below the smallest normal double (the reference clips its logarithm there),
+// it takes the logarithmic form with ln y = ln f + ln K (ln f tabulated; K >= 1 where unmasked).
+__device__ __forceinline__ double ec_loglog_gamma(int ks, int khi, double b, const double* s_f,
+                                                  const double* s_lf, const double* s_A,
+                                                  const double* s_G, const double* s_gm,
+                                                  const double* s_idl, const double* s_lr) {
+    double y_prev = 0.0, z_prev = 0.0, K_prev = 1.0, a = 0.0;
+    for (int k = ks; k <= khi; ++k) {
+        const double f = s_f[k];
+        double y = 0.0, z = 0.0, K = 1.0;
+        if (f != 0.0) {
+            const double t = s_G[k] * b;
+            K = fma(t, t - 2.0, s_A[k]);
+            y = f * K;
+            z = s_gm[k] * y;
+        }
+        if (k > ks && y != 0.0 && y_prev != 0.0) {  // a zero end point switches the interval off (:112-117)
+            bool ok;
+            double v = loglog_interval_z(z_prev, z, s_lr[k - 1], ok);
+            if (!ok || y < kTiny || y_prev < kTiny) {
+                const double ly = (y >= kTiny) ? s_lf[k] + log(K) : clipped_log(y);
+                const double lyp = (y_prev >= kTiny) ? s_lf[k - 1] + log(K_prev) : clipped_log(y_prev);
+                v = loglog_interval_pre(s_gm[k - 1], s_gm[k], s_idl[k - 1], s_lr[k - 1], y_prev, y, lyp, ly);
+            }
+            a += v;
+        }
+        y_prev = y;
+        z_prev = z;
+        K_prev = K;
+    }
+    return a;
+}
+
 template <int INTEG, int J>
 __global__ void __launch_bounds__(256) ec_main_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
@@ -407,9 +443,11 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
     const double* a_b = a_omc + n_pairs;
     const double* a_W = a_b + n_pairs;
     const double* a_c = a_W + n_pairs;
+    const double* a_omc_p = a_c + n_pairs;  // mirror partner of a folded pair (W_p = 0: none)
+    const double* a_W_p = a_omc_p + n_pairs;
     for (int slice = blockIdx.x; slice < S; slice += gridDim.x) {
         double b[J], W[J], c[J], acc[J];
-        int lo[J], hi[J];
+        int lo[J], hi[J], lo_p[J];
 #pragma unroll
         for (int jj = 0; jj < J; ++jj) {
             int j = slice * (T * J) + jj * T + tid;
@@ -442,10 +480,15 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
             bool doubt = (k < n_gamma && (fabs(Ga - cj) <= band || Aa > 1e8)) ||
                          (k > 0 && (fabs(Gb - cj) <= band || (Ab > 1e8 && Gb < kFmax)));
             doubt = (doubt || !(cj < kFmax)) && cj > 0.0;
+            lo_p[jj] = -1;
             if (doubt) {
                 int j = slice * (T * J) + jj * T + tid;
-                k = first_unmasked_exact(g_gm, n_gamma, a_eps[j], nu_to_eps(nu[i], models[m].z, 1.0),
-                                         a_omc[j]);
+                const double eps_s = nu_to_eps(nu[i], models[m].z, 1.0);
+                k = first_unmasked_exact(g_gm, n_gamma, a_eps[j], eps_s, a_omc[j]);
+                if (INTEG == AGNPY_INTEG_LOGLOG && a_W_p[j] != 0.0) {
+                    const int kp = first_unmasked_exact(g_gm, n_gamma, a_eps[j], eps_s, a_omc_p[j]);
+                    if (kp != k) lo_p[jj] = kp;
+                }
             }
             lo[jj] = k;
             if (cj > 0.0) { kmin = min(kmin, k); kmax = max(kmax, k); }
@@ -480,24 +523,18 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
             } else {
 #pragma unroll
                 for (int jj = 0; jj < J; ++jj) {
-                    int ks = max(lo[jj], klo);
-                    double y_prev = 0.0, ly_prev = 0.0, a = 0.0;
-                    for (int k = ks; k <= khi; ++k) {
-                        double f = s_f[k];
-                        double y = 0.0, ly = 0.0;
-                        if (f != 0.0) {
-                            double t = s_G[k] * b[jj];
-                            double K = fma(t, t - 2.0, s_A[k]);
-                            y = f * K;
-                            ly = clipped_log(y);
-                        }
-                        if (k > ks)
-                            a += loglog_interval_pre(s_gm[k - 1], s_gm[k], s_idl[k - 1], s_lr[k - 1],
-                                                     y_prev, y, ly_prev, ly);
-                        y_prev = y;
-                        ly_prev = ly;
+                    acc[jj] = ec_loglog_gamma(max(lo[jj], klo), khi, b[jj], s_f, s_lf, s_A, s_G, s_gm, s_idl,
+                                              s_lr);
+                    // folded phi axis: a mirror partner whose own decision (inside the guard band)
+                    // starts at another index gets its own gamma integral
+                    if (lo_p[jj] >= 0) {
+                        const double a_p = ec_loglog_gamma(max(lo_p[jj], klo), khi, b[jj], s_f, s_lf, s_A, s_G,
+                                                           s_gm, s_idl, s_lr);
+                        const int j = slice * (T * J) + jj * T + tid;
+                        const double W_p = a_W_p[j];
+                        // W acc stands for (W - W_p) acc + W_p a_p
+                        acc[jj] = acc[jj] + (W_p / W[jj]) * (a_p - acc[jj]);
                     }
-                    acc[jj] = a;
                 }
             }
 #pragma unroll
@@ -990,7 +1027,7 @@ __global__ void __launch_bounds__(128) ec_finish_kernel(
 // whose threshold lies within 3 units of the high word of G_k (>= 1.4e-6 relative) are taken out
 // of the prefix and decided one by one with the reference's own formula (kernels.py:36-40), mirror
 // partners of a folded phi axis separately -- only the association order of the sums differs
-// (measured <= 1e-13 from the oracle, tests/test_gpu_prefix.py).
+// (measured <= 1e-15 from the direct kernel on the BASELINE configs, tests/test_gpu_prefix.py).
 //
 // ec_moments_kernel: grid = (segments, models), 1024 threads: exclusive prefix sums of W, W b, W b^2
 //                    over each sorted 1024-pair segment + the high words of c (dead pairs: INT_MIN)
@@ -1213,10 +1250,12 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
     // mirror-symmetric phi grid (the caller vouches for it): one table entry per mirror pair, if
     // the folded (mu, phi) table still feeds the polynomial kernel
-    if (fold_req && integ == AGNPY_INTEG_TRAPZ && n_phi >= 2 &&
+    if (fold_req && n_phi >= 2 &&
         (variant == AGNPY_EC_ISO_MONO || variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR)) {
         EcPlan pf = ec_plan(variant, n_mu, (n_phi + 1) / 2, integ);
-        if (prefix || pf.n_pairs >= 512) p = pf;
+        // np.trapz: only where the folded table still feeds the polynomial kernel (the small-table
+        // kernel does not carry the partner bookkeeping); trapz_loglog and the prefix path: always
+        if (prefix || integ == AGNPY_INTEG_LOGLOG || pf.n_pairs >= 512) p = pf;
     }
     const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
     // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point

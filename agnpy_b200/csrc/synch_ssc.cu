@@ -267,8 +267,7 @@ int launch_synch(const agnpy_model_t* models, int n_models, const double* nu, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: SSC.  grid = (n_nu, n_models); threads own seed energies eps_j and loop over gamma.
-// Per (gamma_k, nu) the block tabulates in shared memory (kernels.py:17-33 rewritten):
+// K2: SSC.  Per (gamma_k, nu) the kernels tabulate (kernels.py:17-33 rewritten):
 //   u = eps_s/gamma, v = u/(1-u) (= gamma_e q), h = v/(4 gamma)  ->  q = h / eps_j
 //   lh = ln h (ln q = lh - ln eps_j),  c1 = 1 + v^2/(2(1+v)),  q_min = 1/(4 gamma^2)
 //   F_c = 2 q ln q + (1-q)(c1 + 2q)
@@ -291,125 +290,100 @@ __device__ __forceinline__ double Fc_exact(double g, double eps, double eps_s, b
 
 constexpr double kGuard = 1e-12;
 
-template <int INTEG>
-__global__ void __launch_bounds__(256) ssc_kernel(
+// K2, trapz_loglog (utils/math.py:55-119 on both axes, synchrotron_self_compton.py:154-155): one block
+// of 8 warps per (nu, model); warp w takes the seed energies j = w, w + 8, ...  The gamma axis runs
+// across the lanes: lane l of group g owns gamma_k, k = 31 g + l, evaluates y = N_e/gamma^2 F_c and
+// for seed energy eps_j, takes y of its upper neighbour from lane l + 1 by shuffle and
+// integrates its own interval [gamma_k, gamma_k+1] in the logarithm-free form of common.cuh where it
+// applies (lane 31 only feeds lane 30: groups overlap by one point).  A seed's unmasked gamma range is contiguous, so the lanes of a group work in lockstep -- the
+// earlier one-thread-per-seed kernel had every lane on a different part of its own band.  Per seed
+// the lane partials are joined by one shuffle reduction; the outer eps integral is taken at the end.
+// Per-(gamma, nu) tables (h, ln h, c1, guarded q_min, interval constants) are built once per block in
+// shared memory; the masks are decided as in the np.trapz kernel (guard band + the reference's own
+// operation order inside it).
+constexpr int kSscLogWarps = 8;
+__global__ void __launch_bounds__(32 * kSscLogWarps) ssc_loglog_kernel(
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
     const double* __restrict__ tab, int n_gamma, const double* __restrict__ U_seed,
     const double* __restrict__ eps_seed, int n_seed, double* __restrict__ out) {
     extern __shared__ double sh[];
     __shared__ double red[32];
-    const int m = blockIdx.y, i = blockIdx.x;
+    const int m = blockIdx.y, i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const agnpy_model_t& M = models[m];
     const double* gs = tab + (size_t)m * 3 * n_gamma;
     const double* Ne = gs + n_gamma;
     const double eps_s = nu_to_eps(nu[i], M.z, M.delta_D);
-    double* s_g = sh;                  // gamma_k
-    double* s_f = s_g + n_gamma;       // trapz: w_k N_e/gamma^2 ; loglog: N_e/gamma^2
+    double* s_g = sh;
+    double* s_f = s_g + n_gamma;       // N_e / gamma^2
     double* s_h = s_f + n_gamma;
     double* s_lh = s_h + n_gamma;
     double* s_c1 = s_lh + n_gamma;
     double* s_qlo = s_c1 + n_gamma;    // q_min (1+guard): surely inside above this
     double* s_qlo2 = s_qlo + n_gamma;  // q_min (1-guard): surely outside below this
-    double* s_idl = s_qlo2 + n_gamma;  // loglog only: 1/(ln g_k - ln g_k+1)
-    double* s_lr = s_idl + n_gamma;    // loglog only: ln(g_k+1/g_k)
-    double* s_Y = s_lr + n_gamma;      // loglog only: [n_seed] gamma-integrals
-    // trapz only: the same tables interleaved as double2 {f,h} {ln h,c1} {q_lo,q_lo2}; placed at
-    // an even double offset so the 16-byte loads are aligned (dynamic smem is 16-byte aligned)
-    double* s_pack = sh + ((7 * n_gamma + 1) & ~1);
+    double* s_idl = s_qlo2 + n_gamma;  // 1/(ln g_k - ln g_k+1)
+    double* s_lr = s_idl + n_gamma;    // ln(g_k+1/g_k)
+    double* s_Y = s_lr + n_gamma;      // [n_seed] U_j x gamma-integral
+    const double* Us = U_seed + (size_t)m * n_seed;
+    const double* es = eps_seed + (size_t)m * n_seed;
     for (int k = threadIdx.x; k < n_gamma; k += blockDim.x) {
         double g = gs[k];
-        double f = Ne[k] / (g * g);
-        if (INTEG == AGNPY_INTEG_TRAPZ) f = f * trapz_weight(gs, k, n_gamma);
         double u = eps_s / g;
         double v = u / (1.0 - u);
         double h = v / (4.0 * g);
         double qmin = 1.0 / (4.0 * (g * g));
         s_g[k] = g;
-        s_f[k] = f;
+        s_f[k] = Ne[k] / (g * g);
         s_h[k] = h;
         s_lh[k] = log(h);
         s_c1[k] = 1.0 + 0.5 * (v * v) / (1.0 + v);
         s_qlo[k] = qmin * (1.0 + kGuard);
         s_qlo2[k] = qmin * (1.0 - kGuard);
-        if (INTEG == AGNPY_INTEG_TRAPZ) {
-            s_pack[2 * k] = f;
-            s_pack[2 * k + 1] = h;
-            s_pack[2 * n_gamma + 2 * k] = log(h);
-            s_pack[2 * n_gamma + 2 * k + 1] = 1.0 + 0.5 * (v * v) / (1.0 + v);
-            s_pack[4 * n_gamma + 2 * k] = qmin * (1.0 + kGuard);
-            s_pack[4 * n_gamma + 2 * k + 1] = qmin * (1.0 - kGuard);
-        }
-        if (INTEG == AGNPY_INTEG_LOGLOG && k < n_gamma - 1) {
+        if (k < n_gamma - 1) {
             double gu = gs[k + 1];
             s_idl[k] = 1.0 / (clipped_log(g) - clipped_log(gu));
             s_lr[k] = clipped_log(gu / g);
         }
     }
     __syncthreads();
-    const double* Us = U_seed + (size_t)m * n_seed;
-    const double* es = eps_seed + (size_t)m * n_seed;
-    double total = 0.0;
-    for (int j = threadIdx.x; j < n_seed; j += blockDim.x) {
+    for (int j = warp; j < n_seed; j += kSscLogWarps) {
         const double eps = es[j];
-        const double ie = 1.0 / eps;
-        const double lie = -log(eps);
+        const double ie = 1.0 / eps, lie = -log(eps);
         double acc = 0.0;
-        if (INTEG == AGNPY_INTEG_TRAPZ) {
-            // hot loop reads {f, h}, {ln h, c1}, {q_lo, q_lo2} as three 16-byte broadcasts
-            const double2* p_fh = reinterpret_cast<const double2*>(s_pack);
-            const double2* p_lc = p_fh + n_gamma;
-            const double2* p_qq = p_lc + n_gamma;
-            for (int k = 0; k < n_gamma; ++k) {
-                double2 fh = p_fh[k];
-                if (fh.x == 0.0) continue;  // block-uniform: outside the electron distribution
-                double q = fh.y * ie;
-                double2 qq = p_qq[k];
-                if (q >= qq.x && q <= 1.0 - kGuard) {
-                    double2 lc = p_lc[k];
-                    double lq = lc.x + lie;
-                    double F = fma(q + q, lq, (1.0 - q) * fma(2.0, q, lc.y));
-                    acc = fma(fh.x, F, acc);
-                } else if (q >= qq.y && q <= 1.0 + kGuard) {
-                    bool in;
-                    double F = Fc_exact(s_g[k], eps, eps_s, in);
-                    if (in) acc = fma(fh.x, F, acc);
-                }
+        for (int k0 = 0; k0 < n_gamma - 1; k0 += 31) {
+            const int k = k0 + lane;
+            const bool in = k < n_gamma;
+            const double f = in ? s_f[k] : 0.0;
+            const double q = in ? s_h[k] * ie : 0.0;
+            const bool sure = f != 0.0 && q >= s_qlo[in ? k : 0] && q <= 1.0 - kGuard;
+            const bool maybe = f != 0.0 && !sure && q >= s_qlo2[in ? k : 0] && q <= 1.0 + kGuard;
+            if (!__any_sync(0xffffffffu, sure || maybe)) continue;  // the whole group is masked
+            double y = 0.0;
+            if (sure) {
+                const double lq = s_lh[k] + lie;
+                y = f * fma(q + q, lq, (1.0 - q) * fma(2.0, q, s_c1[k]));
+            } else if (maybe) {
+                bool inside;
+                const double F = Fc_exact(s_g[k], eps, eps_s, inside);
+                y = inside ? f * F : 0.0;
             }
-            double w = trapz_weight(es, j, n_seed);
-            total = fma(w * Us[j], acc, total);
-        } else {
-            // gamma axis by trapz_loglog, carried sequentially (utils/math.py:55-119)
-            double y_prev = 0.0, ly_prev = 0.0;
-            for (int k = 0; k < n_gamma; ++k) {
-                double f = s_f[k];
-                double y = 0.0;
-                if (f != 0.0) {
-                    double q = s_h[k] * ie;
-                    if (q >= s_qlo[k] && q <= 1.0 - kGuard) {
-                        double lq = s_lh[k] + lie;
-                        y = f * fma(q + q, lq, (1.0 - q) * fma(2.0, q, s_c1[k]));
-                    } else if (q >= s_qlo2[k] && q <= 1.0 + kGuard) {
-                        bool in;
-                        double F = Fc_exact(s_g[k], eps, eps_s, in);
-                        y = in ? f * F : 0.0;
-                    }
-                }
-                double ly = (y != 0.0) ? clipped_log(y) : 0.0;
-                if (k > 0)
-                    acc += loglog_interval_pre(s_g[k - 1], s_g[k], s_idl[k - 1], s_lr[k - 1], y_prev, y,
-                                               ly_prev, ly);
-                y_prev = y;
-                ly_prev = ly;
+            const double y_up = __shfl_down_sync(0xffffffffu, y, 1);
+            if (lane < 31 && k < n_gamma - 1 && y != 0.0 && y_up != 0.0) {  // zero end point: no interval
+                bool ok;
+                double v = loglog_interval_z(s_g[k] * y, s_g[k + 1] * y_up, s_lr[k], ok);
+                if (!ok || y < kTiny || y_up < kTiny)  // far apart, or clipped by the reference: logs
+                    v = loglog_interval_pre(s_g[k], s_g[k + 1], s_idl[k], s_lr[k], y, y_up, clipped_log(y),
+                                            clipped_log(y_up));
+                acc += v;
             }
-            s_Y[j] = Us[j] * acc;
         }
+        acc = warp_sum(acc);
+        if (lane == 0) s_Y[j] = Us[j] * acc;
     }
-    if (INTEG == AGNPY_INTEG_LOGLOG) {
-        __syncthreads();
-        for (int j = threadIdx.x; j < n_seed - 1; j += blockDim.x)
-            total += loglog_interval(es[j], es[j + 1], s_Y[j], s_Y[j + 1], clipped_log(s_Y[j]),
-                                     clipped_log(s_Y[j + 1]));
-    }
+    __syncthreads();
+    double total = 0.0;
+    for (int j = threadIdx.x; j < n_seed - 1; j += blockDim.x)
+        total += loglog_interval(es[j], es[j + 1], s_Y[j], s_Y[j + 1], clipped_log(s_Y[j]),
+                                 clipped_log(s_Y[j + 1]));
     total = block_sum(total, red);
     if (threadIdx.x == 0) {
         // synchrotron_self_compton.py:156-158
@@ -613,13 +587,12 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
     }
     dim3 grid(n_nu, n_models);
     size_t smem = (9 * (size_t)n_gamma + n_seed) * sizeof(double);
-    if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for ssc kernel");
+    if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for the SSC trapz_loglog kernel");
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(ssc_kernel<AGNPY_INTEG_LOGLOG>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ssc_loglog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     timing_begin(stream);
-    ssc_kernel<AGNPY_INTEG_LOGLOG><<<grid, 256, smem, stream>>>(
-        models, nu, n_nu, tab, n_gamma, U_seed, eps_seed, n_seed, out);
+    ssc_loglog_kernel<<<grid, 32 * kSscLogWarps, smem, stream>>>(models, nu, n_nu, tab, n_gamma, U_seed,
+                                                                  eps_seed, n_seed, out);
     timing_end(stream);
     note_launch();
     return AGNPY_OK;

@@ -45,12 +45,16 @@ def _cpu_compute(nu):
     return f
 
 
-def _worker(rank, world, port, n_models, q):
+def _worker(rank, world, port, n_models, q, gather="all"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     nu = np.logspace(9, 18, 12)
-    out = sharded_evaluate(_cpu_compute(nu), _models(n_models), nu.size, device="cpu")
-    q.put((rank, out.numpy().copy()))
+    from agnpy_b200.batch import GatherBuffers
+    buffers = GatherBuffers()
+    for _ in range(2):      # the second call reuses the staging buffers of the first
+        out = sharded_evaluate(_cpu_compute(nu), _models(n_models), nu.size, device="cpu",
+                               gather=gather, buffers=buffers)
+    q.put((rank, None if out is None else out.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +78,35 @@ def test_sharded_evaluate_world2_gloo(n_models):
     for r in range(2):
         assert results[r].shape == (n_models, nu.size)
         np.testing.assert_array_equal(results[r], full)   # every rank holds the whole batch
+
+
+@pytest.mark.parametrize("gather", ["rank0", "none"])
+def test_gather_modes_world2_gloo(gather):
+    """gather="rank0": the same collective, only rank 0 returns the batch (the others skip their
+    device->host copy); gather="none": no collective, every rank returns its own shard"""
+    n_models = 5
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_models, q, gather)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nu = np.logspace(9, 18, 12)
+    full = _cpu_compute(nu)(_models(n_models)).numpy()
+    if gather == "rank0":
+        np.testing.assert_array_equal(results[0], full)
+        assert results[1] is None
+    else:
+        np.testing.assert_array_equal(results[0], full[:3])     # ceil(5/2) models on rank 0
+        np.testing.assert_array_equal(results[1], full[3:])
+    with pytest.raises(ValueError):
+        sharded_evaluate(lambda m: None, _models(2), 12, gather="some")
 
 
 def _nu_worker(rank, world, port, n_nu, q):
