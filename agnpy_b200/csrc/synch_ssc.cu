@@ -323,6 +323,9 @@ __global__ void __launch_bounds__(32 * kSscLogWarps) ssc_loglog_kernel(
     double* s_idl = s_qlo2 + n_gamma;  // 1/(ln g_k - ln g_k+1)
     double* s_lr = s_idl + n_gamma;    // ln(g_k+1/g_k)
     double* s_Y = s_lr + n_gamma;      // [n_seed] U_j x gamma-integral
+    double* s_ie = s_Y + n_seed;       // [n_seed] 1/eps_j
+    double* s_lie = s_ie + n_seed;     // [n_seed] -ln eps_j
+    const int n_groups = (n_gamma - 1 + 30) / 31;  // groups of 31 intervals
     const double* Us = U_seed + (size_t)m * n_seed;
     const double* es = eps_seed + (size_t)m * n_seed;
     for (int k = threadIdx.x; k < n_gamma; k += blockDim.x) {
@@ -344,40 +347,89 @@ __global__ void __launch_bounds__(32 * kSscLogWarps) ssc_loglog_kernel(
             s_lr[k] = clipped_log(gu / g);
         }
     }
+    for (int j = threadIdx.x; j < n_seed; j += blockDim.x) {  // per-seed constants, once per block
+        s_ie[j] = 1.0 / es[j];
+        s_lie[j] = -log(es[j]);
+    }
     __syncthreads();
-    for (int j = warp; j < n_seed; j += kSscLogWarps) {
-        const double eps = es[j];
-        const double ie = 1.0 / eps, lie = -log(eps);
-        double acc = 0.0;
-        for (int k0 = 0; k0 < n_gamma - 1; k0 += 31) {
-            const int k = k0 + lane;
-            const bool in = k < n_gamma;
-            const double f = in ? s_f[k] : 0.0;
-            const double q = in ? s_h[k] * ie : 0.0;
-            const bool sure = f != 0.0 && q >= s_qlo[in ? k : 0] && q <= 1.0 - kGuard;
-            const bool maybe = f != 0.0 && !sure && q >= s_qlo2[in ? k : 0] && q <= 1.0 + kGuard;
-            if (!__any_sync(0xffffffffu, sure || maybe)) continue;  // the whole group is masked
-            double y = 0.0;
-            if (sure) {
-                const double lq = s_lh[k] + lie;
-                y = f * fma(q + q, lq, (1.0 - q) * fma(2.0, q, s_c1[k]));
-            } else if (maybe) {
-                bool inside;
-                const double F = Fc_exact(s_g[k], eps, eps_s, inside);
-                y = inside ? f * F : 0.0;
+    // two seeds per pass (j and j + 8): the per-gamma tables are read once for both and the two
+    // chains of dependent FP64 operations overlap
+    for (int j = warp; j < n_seed; j += 2 * kSscLogWarps) {
+        const int jb = j + kSscLogWarps;
+        const bool two = jb < n_seed;
+        const double eps[2] = {es[j], two ? es[jb] : es[j]};
+        const double ie[2] = {s_ie[j], two ? s_ie[jb] : s_ie[j]};
+        const double lie[2] = {s_lie[j], two ? s_lie[jb] : s_lie[j]};
+        // the unmasked gamma range of a seed is contiguous: q = h_k / eps_j falls with k (q <= 1 from
+        // some k1 on) and q / q_min = 4 gamma_k^2 h_k / eps_j falls towards eps_s / eps_j (q >= q_min up
+        // to some k2).  One probe per group start (lane g tests entry 31 g) brackets it, so most groups
+        // that are masked as a whole are never visited (the bracket is conservative: the group test
+        // below still skips an empty first or last group).
+        int g_first = 0, g_last = n_groups - 1;
+        if (n_groups <= 32) {
+            const int kp = min(lane * 31, n_gamma - 1);
+            const bool probe = lane < n_groups;
+            const double hp = s_h[kp];
+            int gf = n_groups, gl = -1;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const double qp = hp * ie[t];
+                // masked on the low-gamma side: gamma <= eps_s (h <= 0 or not finite) or q > 1
+                const unsigned above = __ballot_sync(0xffffffffu, probe && (!(hp > 0.0) || !(qp <= 1.0 + kGuard)));
+                // masked on the high-gamma side: q < q_min
+                const unsigned below = __ballot_sync(0xffffffffu, probe && hp > 0.0 && qp < s_qlo2[kp]);
+                gf = min(gf, above ? 31 - __clz(above) : 0);                 // lower edge in or after this group
+                gl = max(gl, below ? __ffs(below) - 2 : n_groups - 1);  // upper edge before this group's start
             }
-            const double y_up = __shfl_down_sync(0xffffffffu, y, 1);
-            if (lane < 31 && k < n_gamma - 1 && y != 0.0 && y_up != 0.0) {  // zero end point: no interval
-                bool ok;
-                double v = loglog_interval_z(s_g[k] * y, s_g[k + 1] * y_up, s_lr[k], ok);
-                if (!ok || y < kTiny || y_up < kTiny)  // far apart, or clipped by the reference: logs
-                    v = loglog_interval_pre(s_g[k], s_g[k + 1], s_idl[k], s_lr[k], y, y_up, clipped_log(y),
-                                            clipped_log(y_up));
-                acc += v;
+            g_first = gf;
+            g_last = gl;
+        }
+        double acc[2] = {0.0, 0.0};
+        for (int g = g_first; g <= g_last; ++g) {
+            const int k = g * 31 + lane;
+            const bool in = k < n_gamma;
+            const int kk = in ? k : 0;
+            const double f = in ? s_f[kk] : 0.0, h = s_h[kk], qlo = s_qlo[kk], qlo2 = s_qlo2[kk];
+            double q[2];
+            bool sure[2], maybe[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                q[t] = in ? h * ie[t] : 0.0;
+                sure[t] = f != 0.0 && q[t] >= qlo && q[t] <= 1.0 - kGuard;
+                maybe[t] = f != 0.0 && !sure[t] && q[t] >= qlo2 && q[t] <= 1.0 + kGuard;
+            }
+            if (!__any_sync(0xffffffffu, sure[0] || maybe[0] || sure[1] || maybe[1])) continue;  // all masked
+            const double lh = s_lh[kk], c1 = s_c1[kk], gk = s_g[kk];
+            const double gu = s_g[min(kk + 1, n_gamma - 1)], lr = s_lr[kk];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                double y = 0.0;
+                if (sure[t]) {
+                    const double lq = lh + lie[t];
+                    y = f * fma(q[t] + q[t], lq, (1.0 - q[t]) * fma(2.0, q[t], c1));
+                } else if (maybe[t]) {
+                    bool inside;
+                    const double F = Fc_exact(gk, eps[t], eps_s, inside);
+                    y = inside ? f * F : 0.0;
+                }
+                const double y_up = __shfl_down_sync(0xffffffffu, y, 1);
+                if (lane < 31 && k < n_gamma - 1 && y != 0.0 && y_up != 0.0) {  // zero end point: no interval
+                    bool ok;
+                    double v = loglog_interval_z(gk * y, gu * y_up, lr, ok);
+                    if (!ok || y < kTiny || y_up < kTiny)  // far apart, or clipped by the reference: logs
+                        v = loglog_interval_pre(gk, gu, s_idl[kk], lr, y, y_up, clipped_log(y), clipped_log(y_up));
+                    acc[t] += v;
+                }
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) s_Y[j] = Us[j] * acc;
+        // both lane sums in one butterfly: after the first exchange a lane carries one of the two
+        const bool upper = (lane & 16) != 0;
+        double mine = upper ? acc[1] : acc[0], other = upper ? acc[0] : acc[1];
+        mine += __shfl_xor_sync(0xffffffffu, other, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) s_Y[j] = Us[j] * mine;
+        if (lane == 16 && two) s_Y[jb] = Us[jb] * mine;
     }
     __syncthreads();
     double total = 0.0;
@@ -586,7 +638,7 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
         return AGNPY_OK;
     }
     dim3 grid(n_nu, n_models);
-    size_t smem = (9 * (size_t)n_gamma + n_seed) * sizeof(double);
+    size_t smem = (9 * (size_t)n_gamma + 3 * (size_t)n_seed) * sizeof(double);
     if (smem > 200 * 1024) return fail(AGNPY_ERR_ARG, "n_gamma/n_seed too large for the SSC trapz_loglog kernel");
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(ssc_loglog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
