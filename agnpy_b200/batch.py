@@ -48,7 +48,7 @@ def local_slice(n_models, world_size, rank):
     return lo, hi, per_rank
 
 
-GATHER_MODES = ("all", "rank0", "none")
+GATHER_MODES = ("all", "rank0", "none", "host")
 
 
 class GatherBuffers:
@@ -70,6 +70,102 @@ class GatherBuffers:
         return self.block, self.out
 
 
+class HostGather:
+    """gather="host": the ranks of ONE node assemble the batch in host memory, not on the device.
+
+    When the consumer of the SEDs is host code (a sampler, a likelihood), the device all-gather plus
+    a device->host copy of the WHOLE batch on every rank is wasted motion: here every rank copies
+    only its own shard device->host, straight into its rows of one block of shared memory (a file in
+    /dev/shm) that all ranks map (registered with CUDA, so the copy is an asynchronous pinned transfer), and a
+    sequence-number barrier in the same segment tells everyone when all shards have landed.  Bytes
+    over PCIe per rank: those of its shard, as at N = 1; no collective on the data path.
+
+    Two blocks are used alternately: the block of call k is rewritten at call k + 2, and no rank can
+    enter call k + 2 before every rank has entered call k + 1 (the barrier), i.e. has finished with
+    the views handed out by call k -- the same "valid until the next call" rule as the pinned block
+    of a single rank."""
+
+    def __init__(self, group, rows, cols, register=True):
+        import torch
+        import torch.distributed as dist
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows, self.cols, self.group = rows, cols, group
+        hosts = [None] * self.world
+        import socket
+        dist.all_gather_object(hosts, socket.gethostname(), group=group)
+        if len(set(hosts)) != 1:
+            raise RuntimeError("gather='host' needs all ranks on one node; use gather='all'")
+        block = rows * cols * 8
+        size = 2 * block + 64 * self.world + 64
+        # a file in /dev/shm mapped by every rank (plain mmap: the mapping lives as long as the numpy
+        # views do, and the name is unlinked as soon as everybody has it open)
+        import mmap
+        import os
+        path = [None]
+        if self.rank == 0:
+            path[0] = f"/dev/shm/agnpy_b200_{os.getpid()}_{id(self):x}"
+            fd = os.open(path[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, size)
+        dist.broadcast_object_list(path, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                                   group=group)
+        if self.rank != 0:
+            fd = os.open(path[0], os.O_RDWR)
+        self._mmap = mmap.mmap(fd, size)
+        os.close(fd)
+        self._path = path[0]
+        buf = self._mmap
+        self.blocks = [np.frombuffer(buf, dtype=np.float64, count=rows * cols, offset=b * block)
+                       .reshape(rows, cols) for b in range(2)]
+        # one cache line per rank: the sequence number of the last call whose shard has landed
+        self.flags = np.frombuffer(buf, dtype=np.int64, count=8 * self.world, offset=2 * block)
+        self.seq = 0
+        self._registered = False
+        if register and torch.cuda.is_available():
+            ptr = self.blocks[0].ctypes.data
+            rc = torch.cuda.cudart().cudaHostRegister(ptr, 2 * block, 0)
+            self._registered = int(rc) == 0
+            self._ptr = ptr
+        self.tensors = [torch.from_numpy(b) for b in self.blocks]
+        dist.barrier(group=group)       # everyone has mapped the file before rank 0 unlinks it
+        if self.rank == 0:
+            os.unlink(self._path)       # the mappings stay alive; the name is freed at once
+
+    def block(self):
+        """(torch view, numpy view) of the block of the call that is about to be made"""
+        b = (self.seq + 1) & 1
+        return self.tensors[b], self.blocks[b]
+
+    def publish_and_wait(self):
+        """this rank's shard is in place: announce it, wait for everybody else's"""
+        self.seq += 1
+        self.flags[8 * self.rank] = self.seq
+        others = self.flags[::8]
+        while int(others.min()) < self.seq:
+            pass
+
+    def close(self):
+        try:
+            if self._registered:
+                import torch
+                torch.cuda.cudart().cudaHostUnregister(self._ptr)
+            self.tensors = self.blocks = self.flags = None   # the mapping goes with its last view
+        except Exception:
+            pass
+
+
+def host_sharded_evaluate(local_compute, models, n_nu, hg, stream_sync=None):
+    """gather="host" (see HostGather): returns the numpy view [n, n_nu] of the shared block"""
+    n = len(models)
+    lo, hi, per_rank = local_slice(n, hg.world, hg.rank)
+    t_block, np_block = hg.block()
+    if hi > lo:
+        t_block[lo:hi].copy_(local_compute(models[lo:hi]), non_blocking=True)
+    if stream_sync is not None:
+        stream_sync()
+    hg.publish_and_wait()
+    return np_block[:n]
+
+
 def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu", gather="all",
                      buffers=None):
     """Run `local_compute(models[lo:hi]) -> tensor [hi-lo, n_nu]` on this rank's shard and join the
@@ -77,10 +173,15 @@ def sharded_evaluate(local_compute, models, n_nu, group=None, device="cpu", gath
     gather = "all":   all-gather, every rank returns the full [n, n_nu] (default);
              "rank0": the same collective, but only rank 0 returns the result (the others None) -- the
                       caller on the other ranks skips the device->host copy;
-             "none":  no collective: every rank returns its own shard [hi-lo, n_nu]."""
+             "none":  no collective: every rank returns its own shard [hi-lo, n_nu].
+    (gather="host" -- the batch assembled in node-shared host memory, no device collective -- is a mode
+    of the host-level calls, see HostGather.)"""
     import torch.distributed as dist
     if gather not in GATHER_MODES:
         raise ValueError(f"gather must be one of {GATHER_MODES}")
+    if gather == "host":
+        raise ValueError("gather='host' assembles the batch in host memory: use __call__ / "
+                         "host_sharded_evaluate, not the device-side evaluate")
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return local_compute(models)
@@ -282,17 +383,42 @@ class SedBatch:
     def __call__(self, models, gather="all", copy=True):
         """models (host) -> numpy [n_models, n_nu].
         gather: see `sharded_evaluate` ("rank0": ranks != 0 return None and copy nothing back;
-                "none": every rank gets only its own shard).
+                "none": every rank gets only its own shard) and `HostGather` ("host": every rank
+                copies only its own shard device->host, into a block of host memory shared by the
+                ranks of the node; everybody returns the whole batch, no device collective).
         copy=False returns a view of the plan's pinned result block, valid until the next call on
         this plan (saves one host memcpy of the whole result per call)."""
         if models.dtype != _lib.MODEL_DTYPE:
             raise TypeError("models must be a numpy array of agnpy_b200._lib.MODEL_DTYPE")
         with self.torch.cuda.device(self.device):
-            out = self.evaluate_device(models, gather)
+            if gather == "host" and self.shard == "models" and _world(self.group) > 1:
+                return _host_gather_call(self, self._local, models, self.n_nu, copy)
+            out = self.evaluate_device(models, "all" if gather == "host" else gather)
             if out is None:
                 self.torch.cuda.current_stream(self.device).synchronize()
                 return None
             return self._to_host(out, copy)
+
+
+def _world(group):
+    import torch.distributed as dist
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def _host_gather_call(owner, local_compute, items, n_nu, copy):
+    """shared body of SedBatch / FitSedBatch __call__(gather="host"); `owner` keeps the HostGather"""
+    import torch.distributed as dist
+    world = _world(owner.group)
+    per_rank = -(-len(items) // world)
+    hg = getattr(owner, "_host_gather", None)
+    if hg is None or hg.rows < per_rank * world or hg.cols != n_nu:
+        if hg is not None:
+            dist.barrier(group=owner.group)
+            hg.close()
+        hg = owner._host_gather = HostGather(owner.group, per_rank * world, n_nu)
+    sync = owner.torch.cuda.current_stream(owner.device).synchronize
+    out = host_sharded_evaluate(local_compute, items, n_nu, hg, sync)
+    return out.copy() if copy else out
 
 
 class GraphedSum:

@@ -26,7 +26,8 @@ nothing to cache across the per-instrument calls of a gammapy fit that would be 
 import numpy as np
 
 from . import _lib, constants as const, cosmology, grids
-from .batch import GatherBuffers, SedBatch, sharded_evaluate  # GraphedSum: lazily in graphed()
+from .batch import (GatherBuffers, SedBatch, _host_gather_call, _world,  # GraphedSum: lazily in graphed()
+                    sharded_evaluate)
 
 # position (from the end of the spectral block) of the log10-scaled Lorentz factors besides
 # gamma_min / gamma_max, sherpa_wrapper.py:41-48
@@ -208,13 +209,11 @@ class FitSedBatch:
             out = {k: v.cpu().numpy() for k, v in self._local_components(models, 0, n).items()}
         return out
 
-    def evaluate_device(self, pars, d_L=None, gather="all"):
-        """summed SEDs on the device, [B, n_nu] (a buffer of this object: valid until the next call)"""
-        pars = np.atleast_2d(np.asarray(pars, dtype=np.float64))
+    def _local_sum(self, pars, d_L):
+        """closure: index range of this rank's shard -> summed SEDs of those vectors on the device"""
         B = pars.shape[0]
         if d_L is not None:
             d_L = np.broadcast_to(np.asarray(d_L, dtype=np.float64), (B,))
-        index = np.arange(B)
 
         def local(idx):
             # only this rank's shard of the parameter table is turned into model rows
@@ -238,14 +237,25 @@ class FitSedBatch:
                     t["e"].numel(), t["z"].data_ptr(), t["z"].numel(), t["v"].data_ptr(), 1,
                     total.data_ptr(), st), "agnpy_b200_ebl_absorption")
             return total
-        return sharded_evaluate(local, index, self.n_nu, self.group, self.device, gather, self._gather)
+        return local
+
+    def evaluate_device(self, pars, d_L=None, gather="all"):
+        """summed SEDs on the device, [B, n_nu] (a buffer of this object: valid until the next call)"""
+        pars = np.atleast_2d(np.asarray(pars, dtype=np.float64))
+        index = np.arange(pars.shape[0])
+        return sharded_evaluate(self._local_sum(pars, d_L), index, self.n_nu, self.group, self.device,
+                                gather, self._gather)
 
     def __call__(self, pars, d_L=None, gather="all", copy=True):
         """[B, n_par] -> numpy [B, n_nu] (erg cm-2 s-1).  `gather` / `copy` as in SedBatch.__call__:
         the result goes device -> pinned host memory in one asynchronous copy; copy=False returns the
         pinned block itself (valid until the next call)."""
         with self.torch.cuda.device(self.device):
-            out = self.evaluate_device(pars, d_L, gather)
+            if gather == "host" and _world(self.group) > 1:
+                pars = np.atleast_2d(np.asarray(pars, dtype=np.float64))
+                local = self._local_sum(pars, d_L)
+                return _host_gather_call(self, local, np.arange(pars.shape[0]), self.n_nu, copy)
+            out = self.evaluate_device(pars, d_L, "all" if gather == "host" else gather)
             if out is None:
                 self.torch.cuda.current_stream(self.device).synchronize()
                 return None

@@ -109,6 +109,46 @@ def test_gather_modes_world2_gloo(gather):
         sharded_evaluate(lambda m: None, _models(2), 12, gather="some")
 
 
+def _host_worker(rank, world, port, n_models, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from agnpy_b200.batch import HostGather, host_sharded_evaluate
+    nu = np.logspace(9, 18, 12)
+    hg = HostGather(None, 2 * (-(-n_models // world)), nu.size, register=False)
+    outs = []
+    for scale in (1.0, 2.0, 3.0):       # three calls: both blocks of the ping-pong are reused
+        f = _cpu_compute(nu)
+        out = host_sharded_evaluate(lambda m: scale * f(m), _models(n_models), nu.size, hg)
+        outs.append(out.copy())
+    q.put((rank, outs))
+    dist.barrier()
+    hg.close()
+    dist.destroy_process_group()
+
+
+def test_host_gather_world2_gloo():
+    """gather="host": every rank copies its own shard into node-shared host memory; after the
+    sequence barrier every rank sees the whole batch (no collective on the data path)"""
+    n_models = 5
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_host_worker, args=(r, 2, port, n_models, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nu = np.logspace(9, 18, 12)
+    full = _cpu_compute(nu)(_models(n_models)).numpy()
+    for r in range(2):
+        for k, scale in enumerate((1.0, 2.0, 3.0)):
+            np.testing.assert_array_equal(results[r][k], scale * full)
+
+
 def _nu_worker(rank, world, port, n_nu, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
