@@ -13,7 +13,7 @@ inside the timed step.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
 ranks); `e2e` goes through the public host-buffer API (pinned H2D of the model table, D2H of
-the SEDs, wall clock); `roofline` is for the dominant kernel (ec_main_poly7_kernel): `frac` is the
+the SEDs, wall clock); `roofline` is for the dominant kernel (ec_main_poly_kernel): `frac` is the
 EXECUTED FP64 work over the measured DFMA peak, the nominal 16 flop/point figure of SURVEY 8(a) is
 kept beside it as `algorithmic`; `cpu_baseline` is the reference's own code (agnpy v0.5.0 from
 baseline/_ref, on the miniature astropy of oracle/astropy_stub) on one core of this box, or the
@@ -528,7 +528,7 @@ def run_cuda(args):
                                    "agnpy_b200_ec_sed_host)"},
         "integrand_gpts_per_s": total * N_NU * N_GAMMA * N_MU * N_PHI / (ms_per_step * 1e-3) / 1e9,
         "roofline": {
-            "bound": "fp64", "kernel": "ec_main_poly7_kernel (64 threads x 8 pairs)",
+            "bound": "fp64", "kernel": "ec_main_poly_kernel<4,128> (128 threads x 4 sorted pairs, 96 registers, 5 blocks/SM)",
             "achieved": executed, "peak": peak / 1e12, "unit": "TFLOP/s",
             "frac": executed / (peak / 1e12), "traffic": None,
             "what": "EXECUTED FP64 work of the dominant kernel: 2 DFMA (4 flop) per visited integrand "
@@ -549,7 +549,7 @@ def run_cuda(args):
                         "all (gamma,nu)-only / (mu,phi)-only factors are hoisted into tables (2 DFMA "
                         "per point: wf K = P + Q b^2 + R b), points the reference masks to exactly 0 "
                         "are skipped and mirror pairs of the symmetric phi grid share one evaluation"},
-            "traffic_note": "DRAM traffic is not measurable in-run; ncu: profiles/r2*_ec_main_poly7_full.txt "
+            "traffic_note": "DRAM traffic is not measurable in-run; ncu: profiles/r2_all_kernels_full.txt "
                             "(~1.7 % of HBM peak: the path is FP64-pipe bound)"},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                          "sample": f"{n_cpu} SED(s) of the same workload, nu-chunked by 25, 1 thread "

@@ -23,6 +23,19 @@ kw = dict(gamma=g["gamma"], mu=g["mu"], phi=g["phi"])
 single = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", **kw)._local(models).cpu().numpy()
 shard_m = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", group=dist.group.WORLD, **kw)(models)
 out["model_sharding_bit_identical"] = bool(np.array_equal(single, shard_m))
+# the other ways of joining the shards (agnpy_b200.batch.GATHER_MODES)
+sb = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", group=dist.group.WORLD, **kw)
+host = sb(models, gather="host")
+out["gather_host_bit_identical"] = bool(np.array_equal(single, host))
+host2 = sb(models[::-1].copy(), gather="host", copy=False)      # second call: the other half of the block
+out["gather_host_second_call"] = bool(np.array_equal(single[::-1], host2))
+r0 = sb(models, gather="rank0")
+out["gather_rank0"] = bool(np.array_equal(single, r0)) if rank == 0 else r0 is None
+per = -(-len(models) // world)
+mine = sb(models, gather="none")
+out["gather_none_is_own_shard"] = bool(np.array_equal(single[rank * per:(rank + 1) * per], mine))
+pre = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", integrator="trapz_prefix", group=dist.group.WORLD, **kw)
+out["prefix_sharded_rel_dev"] = float(np.max(np.abs(pre(models, gather="host") / single - 1)))
 # config 4 in miniature (1000 gamma, 200 mu, 100 phi would take seconds per rank: use 400 x 120 x 60)
 c = cases.case_c2(n_nu=50 * world + 1, n_gamma=400, n_mu=120, n_phi=60, r=2e17)
 kw4 = dict(gamma=c["gamma"], mu=c["mu"], phi=c["phi"])
@@ -45,8 +58,12 @@ nu = np.logspace(10, 28, 100)
 ref = FitSedBatch(nu, scenario="ec_blr_dt")(pars, cases.D_L_EC)
 got = FitSedBatch(nu, scenario="ec_blr_dt", group=dist.group.WORLD)(pars, cases.D_L_EC)
 out["fit_batch_bit_identical"] = bool(np.array_equal(ref, got))
+got_h = FitSedBatch(nu, scenario="ec_blr_dt", group=dist.group.WORLD)(pars, cases.D_L_EC, gather="host")
+out["fit_batch_host_gather_bit_identical"] = bool(np.array_equal(ref, got_h))
 out["fit_batch_finite_positive"] = bool(np.all(np.isfinite(got)) and got.max() > 0)
-flags = torch.tensor([float(all(v for k, v in out.items() if k != "world"))], device="cuda")
+out["prefix_sharded_ok"] = out["prefix_sharded_rel_dev"] < 1e-12
+flags = torch.tensor([float(all(v for k, v in out.items() if k not in ("world", "prefix_sharded_rel_dev")))],
+                     device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 out["all_ranks_ok"] = bool(flags.item() == 1.0)
 if rank == 0:
