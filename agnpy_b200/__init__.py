@@ -1,5 +1,6 @@
 """agnpy_b200: B200-native (sm_100a, FP64) emission-integral hot path of agnpy behind the
 reference's own Python API.  See DESIGN.md / INTEGRATION.md."""
+from ._lib import strict_reference, strict_reference_mode
 from .absorption import Absorption
 from .compton import ExternalCompton, SynchrotronSelfCompton
 from .ebl import EBL
@@ -16,5 +17,5 @@ __all__ = ["Synchrotron", "ProtonSynchrotron", "SynchrotronSelfCompton", "Extern
            "PowerLaw", "BrokenPowerLaw", "LogParabola", "ExpCutoffPowerLaw", "ExpCutoffBrokenPowerLaw",
            "InterpolatedDistribution",
            "trapz_loglog", "trapz_prefix", "gamma_e_to_integrate", "nu_to_integrate", "mu_to_integrate",
-           "phi_to_integrate", "Quantity", "u"]
+           "phi_to_integrate", "strict_reference", "strict_reference_mode", "Quantity", "u"]
 __version__ = "0.2.0"
