@@ -66,3 +66,33 @@ def test_strict_switch_changes_only_the_two_documented_functions():
     np.testing.assert_array_equal(ec_strict, ec_default)           # EC has no switched function
     assert_parity(tau_strict, STORE["c3_tau_dt"], rtol=RTOL, what="tau_dt strict")
     assert_parity(tau_default, STORE["c3_tau_dt"], rtol=RTOL, what="tau_dt default")
+
+
+def test_drop_in_call_with_ndarray_subclass_quantities():
+    """the argument objects of an astropy user -- ndarray-subclass Quantities, here the ones of the
+    stand-in astropy the reference runs on, in non-CGS units -- give the same numbers as the package's
+    own Quantity and as plain CGS doubles"""
+    from oracle import reference_loader
+    if not reference_loader.available():
+        pytest.skip("needs the stand-in astropy loaded with the reference")
+    reference_loader.load()
+    import astropy.units as au
+    import agnpy_b200 as ab
+    from agnpy_b200 import u
+    nu = np.logspace(15, 26, 40)
+    n_e = ab.BrokenPowerLaw(1e-8 * u.Unit("cm-3"), 2.0, 3.5, 1e4, 20, 5e7)
+    pars_own = (1e-8 * u.Unit("cm-3"), 2.0, 3.5, 1e4, 20, 5e7)
+    pars_sub = (1e-2 * au.Unit("m-3"), 2.0, 3.5, 1e4, 20, 5e7)
+    pc = 3.0856775814913673e18
+    own = ab.ExternalCompton.evaluate_sed_flux_dt(
+        nu * u.Hz, 1.0, 2.0e28 * u.cm, 40, 0.9997, 1e16 * u.cm, 2e46 * u.Unit("erg s-1"), 0.1, 2e-7,
+        1.5e18 * u.cm, 1e18 * u.cm, n_e, *pars_own)
+    sub = ab.ExternalCompton.evaluate_sed_flux_dt(
+        (nu / 1e9) * au.GHz, 1.0, (2.0e28 / pc / 1e6) * au.Mpc, 40, 0.9997, 1e14 * au.m,
+        2e39 * au.W, 0.1, 2e-7, (1.5e18 / pc) * au.pc, 1e16 * au.m, n_e, *pars_sub)
+    plain = ab.ExternalCompton.evaluate_sed_flux_dt(
+        nu, 1.0, 2.0e28, 40, 0.9997, 1e16, 2e46, 0.1, 2e-7, 1.5e18, 1e18, n_e,
+        1e-8, 2.0, 3.5, 1e4, 20, 5e7)
+    np.testing.assert_array_equal(own.value, np.asarray(plain.value))
+    assert_parity(np.asarray(sub.value), np.asarray(own.value), rtol=1e-13, what="non-CGS ndarray-subclass inputs")
+    assert np.max(own.value) > 0
