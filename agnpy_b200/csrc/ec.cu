@@ -687,15 +687,21 @@ __device__ __noinline__ int ec_first_unmasked_ref(const double* __restrict__ gm,
                                                   double nu_i, double z) {
     return first_unmasked_exact(gm, n_gamma, a_eps[j], nu_to_eps(nu_i, z, 1.0), a_omc[j]);
 }
+// 64-bit signed max / min over the warp in two 32-bit REDUX steps (high words, then the low words of
+// the lanes that hold the winning high word) instead of five 64-bit shuffle rounds
 __device__ __forceinline__ long long warp_max_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const unsigned long long w = (unsigned long long)v ^ 0x8000000000000000ull;  // signed -> unsigned order
+    const unsigned h = (unsigned)(w >> 32);
+    const unsigned hi = __reduce_max_sync(0xffffffffu, h);
+    const unsigned lo = __reduce_max_sync(0xffffffffu, h == hi ? (unsigned)w : 0u);
+    return (long long)((((unsigned long long)hi << 32) | lo) ^ 0x8000000000000000ull);
 }
 __device__ __forceinline__ long long warp_min_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const unsigned long long w = (unsigned long long)v ^ 0x8000000000000000ull;
+    const unsigned h = (unsigned)(w >> 32);
+    const unsigned hi = __reduce_min_sync(0xffffffffu, h);
+    const unsigned lo = __reduce_min_sync(0xffffffffu, h == hi ? (unsigned)w : 0xffffffffu);
+    return (long long)((((unsigned long long)hi << 32) | lo) ^ 0x8000000000000000ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -747,16 +753,21 @@ __device__ __forceinline__ int ec_warp_first_le(const long long* __restrict__ s_
     }
     return lo;
 }
-// the same index for the next frequency's table, given the previous one (indices move by a few
-// entries per frequency step): probes at k_prev - 1 + lane; anything else -> full search
-__device__ __forceinline__ int ec_warp_step_le(const long long* __restrict__ s_Gi, int n, long long c,
-                                               int k_prev, int lane) {
-    const int k = k_prev - 1 + lane;
-    const bool gt = k < 0 || (k < n && s_Gi[k] > c);
+// The same indices for the next frequency's table, given the previous ones (they move up by an entry or
+// two per frequency step); anything the 16 probes of a half-warp cannot confirm -> full search.
+// both ends of the window in one probe: lanes 0-15 test entries wlo - 1 + l against cmax, lanes 16-31
+// entries whi - 1 + l against cmin; one load, one compare and one ballot per frequency step
+__device__ __forceinline__ void ec_warp_step_le2(const long long* __restrict__ s_Gi, int n, long long cmax,
+                                                 long long cmin, int& wlo, int& whi, int lane) {
+    const bool upper = lane >= 16;
+    const int k = (upper ? whi : wlo) - 1 + (lane & 15);
+    const bool gt = k < 0 || (k < n && s_Gi[k] > (upper ? cmin : cmax));
     const unsigned bal = __ballot_sync(0xffffffffu, gt);
-    const int cnt = __ffs(~bal) - 1;  // length of the run of set bits from lane 0 (-1: all 32 set)
-    if ((bal & 1u) && cnt > 0) return k_prev - 1 + cnt;
-    return ec_warp_first_le(s_Gi, n, c, lane);
+    const unsigned b0 = bal & 0xffffu, b1 = bal >> 16;
+    const int r0 = __ffs(~b0) - 1, r1 = __ffs(~b1) - 1;  // runs of set bits from the first lane (16: all set)
+    const bool ok0 = (b0 & 1u) && r0 < 16, ok1 = (b1 & 1u) && r1 < 16;
+    wlo = ok0 ? wlo - 1 + r0 : ec_warp_first_le(s_Gi, n, cmax, lane);
+    whi = ok1 ? whi - 1 + r1 : ec_warp_first_le(s_Gi, n, cmin, lane);
 }
 
 template <int J, int T, int MINB>
@@ -838,8 +849,7 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
                 wlo = ec_warp_first_le(s_Gi, n_gamma, cmax, lane);
                 whi = ec_warp_first_le(s_Gi, n_gamma, cmin, lane);
             } else {
-                wlo = ec_warp_step_le(s_Gi, n_gamma, cmax, wlo, lane);
-                whi = ec_warp_step_le(s_Gi, n_gamma, cmin, whi, lane);
+                ec_warp_step_le2(s_Gi, n_gamma, cmax, cmin, wlo, whi, lane);
             }
             // one pass over the window entries: per pair lo = wlo + #{k in [wlo, whi) : G_k > c}
             // (G descending: a prefix count, on high words; a tie there is inside the guard band), and
@@ -910,9 +920,11 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
             }
             kbeg = max(kbeg, klo);
             kmid = min(max(kmid, kbeg), khi + 1);
+            // the b-independent suffix sum at each pair's own first unmasked index seeds its accumulator
+            // (both are exactly 0 past the last electron index): the loads are in flight during phase 1
             double acc[J];
 #pragma unroll
-            for (int jj = 0; jj < J; ++jj) acc[jj] = 0.0;
+            for (int jj = 0; jj < J; ++jj) acc[jj] = s_SP[min(max(lo[jj], klo), n_gamma)];
             // phase 1 (a few steps: the pairs of a warp are neighbours in c): lanes join as the
             // loop passes their first unmasked index
             for (int k = kbeg; k < kmid; ++k) {
@@ -932,12 +944,9 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
                 EC_STEP(q0) EC_STEP(q1) EC_STEP(q2) EC_STEP(q3)
 #undef EC_STEP
             }
-            // every pair adds the b-independent suffix sum at its own first unmasked index (both are
-            // exactly 0 past the last electron index); dead pairs have W = 0
+            // dead pairs have W = 0
 #pragma unroll
-            for (int jj = 0; jj < J; ++jj) {
-                thread_sum = fma(W[jj], acc[jj] + s_SP[min(max(lo[jj], klo), n_gamma)], thread_sum);
-            }
+            for (int jj = 0; jj < J; ++jj) thread_sum = fma(W[jj], acc[jj], thread_sum);
             thread_sum += fold_corr;
         }
         s_sum[(size_t)r * (T + 1) + tid] = thread_sum;
@@ -1190,16 +1199,21 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
     p.J = 1;
     if (integ == AGNPY_INTEG_TRAPZ) {
         p.J = p.n_pairs >= 512 ? 4 : p.n_pairs >= 256 ? 2 : 1;
-        // polynomial kernel (>= 512 pairs): 128 threads x 4 consecutive sorted pairs = 512-pair slices
-        // (2500 folded pairs at the default grids -> 5 slices, 2 % padding), 5 blocks per SM at 96
-        // registers: measured fastest on B200 (scripts/tune_ec.py, profiles/r2*_tune_ec.txt); 8 pairs
-        // per thread widen a warp's index window and lose more in the ragged start than they save
-        if (p.n_pairs >= 512) { p.T = 128; p.J = 4; }
+        // polynomial kernel (>= 512 pairs): 128 threads x 5 (or 4) consecutive sorted pairs, whichever
+        // pads the table less (2500 folded pairs at the default grids -> 4 slices of 640, 2 % padding).
+        // Measured on B200 (scripts/tune_ec.py, profiles/r2_tune_ec.txt): 128 x 5 at 128 registers
+        // (4 blocks per SM, 7 frequencies per block) 2.056 ms per 256 models, 64 x 8 2.076, 128 x 4 at
+        // 96 registers 2.102; larger blocks (160-256 threads) and 10 pairs per thread lose
+        if (p.n_pairs >= 512) {
+            p.T = 128;
+            const int pad5 = (p.n_pairs + 639) / 640 * 640, pad4 = (p.n_pairs + 511) / 512 * 512;
+            p.J = pad5 <= pad4 ? 5 : 4;
+        }
     }
     if (const char* e = getenv("AGNPY_B200_EC_PLAN")) {  // development knob: "T,J"
         int t = 0, j = 0;
         if (sscanf(e, "%d,%d", &t, &j) == 2 && t >= 32 && t <= 256 && t % 32 == 0 &&
-            (j == 1 || j == 2 || j == 4 || j == 8) && (integ == AGNPY_INTEG_TRAPZ || j == 1)) {
+            (j == 1 || j == 2 || j == 4 || j == 5 || j == 8) && (integ == AGNPY_INTEG_TRAPZ || j == 1)) {
             p.T = t;
             p.J = j;
         }
@@ -1258,6 +1272,10 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         if (prefix || integ == AGNPY_INTEG_LOGLOG || pf.n_pairs >= 512) p = pf;
     }
     const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
+    if (use_v4 && p.J == 5) {  // the small-table kernel is instantiated for 1, 2, 4 and 8 pairs per thread
+        p.J = 4;
+        p.S = (p.n_pairs + p.T * p.J - 1) / (p.T * p.J);
+    }
     // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
     // source variants (<= n_phi pairs) stay on the v4 kernel
     const bool v5 = integ == AGNPY_INTEG_TRAPZ && !prefix && !use_v4 && p.n_pairs >= 512;
@@ -1347,7 +1365,7 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     if (v5) {
         const int row_words = ec_row_words(n_gamma);
         // frequencies per block: as many as keep >= 8 waves of blocks in flight, at most 8
-        int L_nu = 8;
+        int L_nu = 16;
         while (L_nu > 1 && (long long)p.S * ((n_nu + L_nu - 1) / L_nu) * n_models < 8LL * 5 * sms) L_nu >>= 1;
         if (const char* e = getenv("AGNPY_B200_EC_LNU")) {  // development knob
             int v = atoi(e);
@@ -1358,10 +1376,9 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         // as the register budget allows (5 x 128 threads at 96 registers, 3 at 8 pairs per thread; 6 of
         // 64 threads x 8 pairs, 8 of 64 x 4)
         const size_t per_nu = row_bytes + 8 + (size_t)(p.T + 1) * sizeof(double);
-        const int blocks_per_sm = p.T >= 128 ? (p.J == 8 ? 3 : 5) : (p.J == 8 ? 6 : 8);
+        const int blocks_per_sm = p.T >= 128 ? (p.J == 8 ? 3 : p.J == 5 ? 4 : 5) : 6;
         const size_t smem_cap = (size_t)(227 * 1024) / blocks_per_sm - 1024;
         if (L_nu * per_nu > smem_cap) L_nu = (int)std::max<size_t>(1, smem_cap / per_nu);
-        L_nu = std::min(L_nu, 8);
         dim3 grid(p.S, (n_nu + L_nu - 1) / L_nu, n_models);
         const size_t smem6 = L_nu * per_nu;
         timing_begin(stream);
@@ -1372,9 +1389,9 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         KERNEL<<<grid, p.T, smem6, stream>>>(models, nu, n_nu, gt, hull, n_gamma, rows, ang,        \
                                              p.n_pairs, p.S, L_nu, part);                           \
     } while (0)
-        if (p.T == 128 && p.J == 4) EC_LAUNCH_K((ec_main_poly_kernel<4, 128, 5>));
+        if (p.T == 128 && p.J == 5) EC_LAUNCH_K((ec_main_poly_kernel<5, 128, 4>));
+        else if (p.T == 128 && p.J == 4) EC_LAUNCH_K((ec_main_poly_kernel<4, 128, 5>));
         else if (p.T == 64 && p.J == 8) EC_LAUNCH_K((ec_main_poly_kernel<8, 64, 6>));
-        else if (p.T == 64 && p.J == 4) EC_LAUNCH_K((ec_main_poly_kernel<4, 64, 8>));
         else if (p.T == 128 && p.J == 8) EC_LAUNCH_K((ec_main_poly_kernel<8, 128, 3>));
         else return fail(AGNPY_ERR_ARG, "ec_sed: unsupported AGNPY_B200_EC_PLAN for the polynomial kernel");
 #undef EC_LAUNCH_K

@@ -528,7 +528,7 @@ def run_cuda(args):
                                    "agnpy_b200_ec_sed_host)"},
         "integrand_gpts_per_s": total * N_NU * N_GAMMA * N_MU * N_PHI / (ms_per_step * 1e-3) / 1e9,
         "roofline": {
-            "bound": "fp64", "kernel": "ec_main_poly_kernel<4,128> (128 threads x 4 sorted pairs, 96 registers, 5 blocks/SM)",
+            "bound": "fp64", "kernel": "ec_main_poly_kernel<5,128> (128 threads x 5 sorted pairs, 128 registers, 4 blocks/SM)",
             "achieved": executed, "peak": peak / 1e12, "unit": "TFLOP/s",
             "frac": executed / (peak / 1e12), "traffic": None,
             "what": "EXECUTED FP64 work of the dominant kernel: 2 DFMA (4 flop) per visited integrand "

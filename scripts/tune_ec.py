@@ -14,7 +14,7 @@ from agnpy_b200.batch import SedBatch
 
 torch.cuda.set_device(0)
 g = bench.grids()
-KNOBS = ("PLAN", "LNU", "NOFOLD")
+KNOBS = ("PLAN", "LNU", "NOFOLD", "MINB6")
 
 
 def run(n_models, reps=8):
