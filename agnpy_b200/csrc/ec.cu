@@ -595,30 +595,44 @@ __device__ __forceinline__ void ec_poly_row_role(
     if (lane < kRowPad) r_QR[n_gamma + lane] = make_double2(0.0, 0.0);
     double carry = 0.0;
     int ill_lo = n_gamma, ill_hi = 0;
-    for (int base = ((n_gamma - 1) >> 5) << 5; base >= 0; base -= 32) {
-        const int k = base + lane;
-        double P = 0.0;
-        if (k < n_gamma) {
-            const double g = gamma[k];
+    // groups of 32 indices from the top of the grid down, four groups per trip: their divisions and
+    // shuffle scans are independent and overlap; only the carry runs through them in order
+    constexpr int kB = 4;
+    for (int base = ((n_gamma - 1) >> 5) << 5; base >= 0; base -= 32 * kB) {
+        double incl[kB];
+#pragma unroll
+        for (int q = 0; q < kB; ++q) {  // straight-line on a clamped index; only the stores are predicated
+            const int k = base - 32 * q + lane;
+            const bool in = k >= 0 && k < n_gamma;
+            const int kk = min(max(k, 0), n_gamma - 1);
+            const double g = gamma[kk];
             const double y = 1.0 - eps_s / g;
             const double A = y + 1.0 / y;
             const double G = (y > 0.0) ? eps_s / ((g * g) * y) : INFINITY;
-            const double wf = g_f[k];
-            const bool live = k >= klo && k <= khi && G < kFmax;
+            const double wf = g_f[kk];
+            const bool live = in && kk >= klo && kk <= khi && G < kFmax;
             const double wG = live ? wf * G : 0.0;  // exactly 0 outside the electron range
-            r_QR[k] = make_double2(wG * G, -2.0 * wG);
-            r_G[k] = G;
-            P = live ? wf * A : 0.0;
-            if (A > 1e8) { ill_lo = min(ill_lo, k); ill_hi = max(ill_hi, k + 1); }
+            if (in) {
+                r_QR[kk] = make_double2(wG * G, -2.0 * wG);
+                r_G[kk] = G;
+                if (A > 1e8) { ill_lo = min(ill_lo, kk); ill_hi = max(ill_hi, kk + 1); }
+            }
+            incl[q] = live ? wf * A : 0.0;
         }
-        double incl = P;  // suffix sum over the lanes of this group
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double v = __shfl_down_sync(0xffffffffu, incl, o);
-            if (lane + o < 32) incl += v;
+        for (int o = 1; o < 32; o <<= 1) {  // suffix sums over the lanes of each group
+#pragma unroll
+            for (int q = 0; q < kB; ++q) {
+                const double v = __shfl_down_sync(0xffffffffu, incl[q], o);
+                if (lane + o < 32) incl[q] += v;
+            }
         }
-        if (k < n_gamma) r_SP[k] = incl + carry;
-        carry += __shfl_sync(0xffffffffu, incl, 0);
+#pragma unroll
+        for (int q = 0; q < kB; ++q) {
+            const int k = base - 32 * q + lane;
+            if (k >= 0 && k < n_gamma) r_SP[k] = incl[q] + carry;
+            carry += __shfl_sync(0xffffffffu, incl[q], 0);
+        }
     }
     ill_lo = __reduce_min_sync(0xffffffffu, ill_lo);
     ill_hi = __reduce_max_sync(0xffffffffu, ill_hi);
