@@ -364,6 +364,61 @@ def _tau_synch(side, A, idx, store=None):
     return _val(ab.tau_on_synchrotron(blob, A.Q(t["nu"], "Hz")))
 
 
+@case("instance_conveniences", rtol=RTOL_EXP_TAIL)
+def _instances(side, A, idx, store=None):
+    """the object-level API on top of the static methods: Blob -> Synchrotron / SSC /
+    ExternalCompton(.set_mu, .set_phi) .sed_flux / .sed_luminosity / .sed_peak_*; Absorption(target, r, z)
+    (.set_mu, .set_phi, .set_l) .tau / .absorption.  One flat vector of everything."""
+    c = cases.case_c1()
+    nu = np.logspace(10, 27, 18)
+    nu_t = cases.case_tau(n_nu=12)["nu"]
+    r_ec, r_tau, z_tau = 2e17, 1.1e16, 0.859
+    n_g, n_mu, n_phi, n_l = 120, 40, 20, 30
+    Gamma = 10
+    mu_s = (1 - 1 / (Gamma * c["delta_D"])) / np.sqrt(1 - 1 / Gamma**2)     # blob.py:110-113
+    if side == "orc":
+        d_L = float(store["instance_conveniences__d_L"])
+        g_blob = np.logspace(np.log10(c["ne_args"][-2]), np.log10(c["ne_args"][-1]), n_g)
+        g_ext = np.logspace(1, 9, n_g)                                       # blob.py:148-151
+        a = (c["z"], d_L, c["delta_D"], c["B"], c["R_b"], c["ne_kind"], c["ne_args"])
+        syn = orc.synch_sed_flux(nu, *a, gamma=g_blob.copy())
+        ssc = orc.ssc_sed_flux(nu, *a, gamma=g_blob.copy())
+        mu, phi = np.linspace(-1, 1, n_mu), np.linspace(0, 2 * np.pi, n_phi)
+        ec = orc.ec_blr_sed_flux(nu, c["z"], d_L, c["delta_D"], mu_s, c["R_b"], cases.L_DISK, cases.XI_LINE,
+                                 cases.EPS_LINE, cases.R_LINE, r_ec, c["ne_kind"], c["ne_args"],
+                                 gamma=g_ext.copy(), mu=mu, phi=phi)
+        ec_dt = orc.ec_dt_sed_flux(nu, c["z"], d_L, c["delta_D"], mu_s, c["R_b"], cases.L_DISK, cases.XI_DT,
+                                   cases.EPS_DT, cases.R_DT, r_ec, c["ne_kind"], c["ne_args"],
+                                   gamma=g_ext.copy(), phi=phi)
+        tau = orc.tau_blr(nu_t, z_tau, 1, cases.L_DISK, cases.XI_LINE, cases.EPS_LINE, cases.R_LINE, r_tau,
+                          l_size=n_l, mu=mu, phi=phi)
+        k = int(np.argmax(syn))
+        return np.concatenate([syn, 4 * np.pi * d_L**2 * syn, [nu[k], syn[k]], ssc, ec, 4 * np.pi * d_L**2 * ec,
+                               ec_dt, tau, np.exp(-tau)])
+    blob = _ref_blob(A, c, gamma_size=n_g, Gamma=Gamma)
+    store["instance_conveniences__d_L"] = np.asarray(blob.d_L.to_value("cm"))
+    nuq, nutq = A.Q(nu, "Hz"), A.Q(nu_t, "Hz")
+    synch = A.agnpy.Synchrotron(blob)
+    ssc = A.agnpy.SynchrotronSelfCompton(blob)
+    blr = A.agnpy.SphericalShellBLR(A.Q(cases.L_DISK, "erg s-1"), cases.XI_LINE, "Lyalpha", A.Q(cases.R_LINE, "cm"))
+    dt = A.agnpy.RingDustTorus(A.Q(cases.L_DISK, "erg s-1"), cases.XI_DT, A.Q(cases.T_DT, "K"),
+                               A.Q(cases.R_DT, "cm"))
+    ec = A.agnpy.ExternalCompton(blob, blr, r=A.Q(r_ec, "cm"))
+    ec.set_mu(n_mu)
+    ec.set_phi(n_phi)
+    ec_dt = A.agnpy.ExternalCompton(blob, dt, r=A.Q(r_ec, "cm"))
+    ec_dt.set_phi(n_phi)
+    ab = A.agnpy.Absorption(blr, r=A.Q(r_tau, "cm"), z=z_tau)
+    ab.set_mu(n_mu)
+    ab.set_phi(n_phi)
+    ab.set_l(n_l)
+    peak = [_val(synch.sed_peak_nu(nuq).to("Hz")), _val(synch.sed_peak_flux(nuq).to("erg cm-2 s-1"))]
+    return np.concatenate([_val(synch.sed_flux(nuq)), _val(synch.sed_luminosity(nuq).to("erg s-1")),
+                           np.ravel(peak), _val(ssc.sed_flux(nuq)), _val(ec.sed_flux(nuq)),
+                           _val(ec.sed_luminosity(nuq).to("erg s-1")), _val(ec_dt.sed_flux(nuq)),
+                           _val(ab.tau(nutq)), _val(ab.absorption(nutq))])
+
+
 @case("ssc_energy_loss_rate")
 def _loss(side, A, idx, store=None):
     c = cases.case_c1()
