@@ -233,7 +233,7 @@ int agnpy_b200_ec_sed(int variant, int n_models, const agnpy_model_t* models, in
     if (ne_kind == AGNPY_NE_TABLE && (!ne_table))
         return fail(AGNPY_ERR_ARG, "ec_sed: AGNPY_NE_TABLE needs an n_e table");
     cudaStream_t stream = (cudaStream_t)stream_;
-    size_t per = ec_workspace_bytes(variant, 1, n_nu, n_gamma, n_mu, n_phi);
+    size_t per = ec_workspace_bytes(variant, 1, n_nu, n_gamma, n_mu, n_phi, integ);
     int chunk = chunk_models(per, n_models);
     double* ws = (double*)workspace(per * chunk, stream);
     if (!ws) return fail(AGNPY_ERR_NOMEM, "ec_sed: workspace");

@@ -423,8 +423,19 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
     double* s_lf = s_gm + n_gamma;   // loglog only
     double* s_idl = s_lf + n_gamma;  // loglog only
     double* s_lr = s_idl + n_gamma;  // loglog only
+    // small tables on the np.trapz path come without the {A, G} table (nt == nullptr): with a few dozen
+    // pairs per (nu, model) it is cheaper to form the two values here than to stream them through HBM
+    const double eps_s_blk = nu_to_eps(nu[i], models[m].z, 1.0);
     for (int k = tid; k < n_gamma; k += T) {
-        double2 ag = AG[k];
+        double2 ag;
+        if (nt != nullptr) {
+            ag = AG[k];
+        } else {  // the arithmetic of ec_nu_role
+            const double g = g_gm[k];
+            const double y = 1.0 - eps_s_blk / g;
+            ag.x = y + 1.0 / y;
+            ag.y = (y > 0.0) ? eps_s_blk / ((g * g) * y) : INFINITY;
+        }
         s_f[k] = g_f[k];
         s_A[k] = ag.x;
         s_G[k] = ag.y;
@@ -1236,23 +1247,60 @@ static EcPlan ec_plan(int variant, int n_mu, int n_phi, int integ) {
     return p;
 }
 
-// doubles of scratch per model
-static size_t ec_words(const EcPlan& p, int n_nu, int n_gamma) {
-    return 5 * (size_t)n_gamma + 2      // gamma tables + hull (2 ints in one double slot, padded)
-           + (kAngCols + kRawCols) * (size_t)p.n_pairs  // pair table (sorted) + unsorted values
-           + 2 * (size_t)n_nu * n_gamma // {A,G}
-           // polynomial rows (np.trapz path) or, in the same area, the prefix moments + sorted high words
-           + std::max((size_t)n_nu * ec_row_words(n_gamma),
-                      (size_t)((p.n_pairs + kPairSeg - 1) / kPairSeg) * 3 * kMomStride + p.n_pairs / 2 + 2)
-           + (size_t)n_nu * p.S * p.W();
+// Which kernels a call runs, and the scratch it needs per model (doubles).  One place decides both, so
+// that the chunking of large batches (capi.cu) sees the real footprint of the path taken: 1.5 MB per
+// model for the polynomial rows at the fit-wrapper grids, 30 KB for a ring torus.
+struct EcPath {
+    EcPlan p;
+    int integ;       // AGNPY_INTEG_TRAPZ / _LOGLOG (flags stripped, prefix mapped to trapz)
+    bool prefix;     // prefix-moment evaluation of the np.trapz integral
+    bool v5;         // polynomial main kernel
+    bool fused_ag;   // small np.trapz table: {A, G} formed inside the main kernel, no table in HBM
+    size_t w_nt, w_rows, w_gt, w_ang, w_raw, w_part;  // words per model of each scratch area
+    size_t words() const { return w_nt + w_rows + w_gt + w_ang + w_raw + w_part + 2; }
+};
+static EcPath ec_path(int variant, int n_nu, int n_gamma, int n_mu, int n_phi, int integ_flags) {
+    EcPath q;
+    const bool fold_req =
+        (integ_flags & AGNPY_INTEG_FOLD_PHI) != 0 && getenv("AGNPY_B200_EC_NOFOLD") == nullptr;
+    int integ = integ_flags & ~AGNPY_INTEG_FOLD_PHI;
+    q.prefix = integ == AGNPY_INTEG_TRAPZ_PREFIX;
+    if (q.prefix) integ = AGNPY_INTEG_TRAPZ;  // same tables (trapz weights folded into wf)
+    q.integ = integ;
+    EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
+    // mirror-symmetric phi grid (the caller vouches for it): one table entry per mirror pair, if
+    // the folded (mu, phi) table still feeds the polynomial kernel
+    if (fold_req && n_phi >= 2 &&
+        (variant == AGNPY_EC_ISO_MONO || variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR)) {
+        EcPlan pf = ec_plan(variant, n_mu, (n_phi + 1) / 2, integ);
+        // np.trapz: only where the folded table still feeds the polynomial kernel (the small-table
+        // kernel does not carry the partner bookkeeping); trapz_loglog and the prefix path: always
+        if (q.prefix || integ == AGNPY_INTEG_LOGLOG || pf.n_pairs >= 512) p = pf;
+    }
+    const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
+    if (use_v4 && p.J == 5) {  // the small-table kernel is instantiated for 1, 2, 4 and 8 pairs per thread
+        p.J = 4;
+        p.S = (p.n_pairs + p.T * p.J - 1) / (p.T * p.J);
+    }
+    // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
+    // source variants (<= n_phi pairs) stay on the small-table kernel
+    q.v5 = integ == AGNPY_INTEG_TRAPZ && !q.prefix && !use_v4 && p.n_pairs >= 512;
+    // np.trapz with a small pair table (ring torus, point source, coarse grids): no {A, G} table in HBM
+    q.fused_ag = integ == AGNPY_INTEG_TRAPZ && !q.prefix && !q.v5 && p.S <= 4;
+    q.p = p;
+    const size_t n_seg = (p.n_pairs + kPairSeg - 1) / kPairSeg;
+    q.w_nt = (q.v5 || q.prefix || q.fused_ag) ? 0 : 2 * (size_t)n_nu * n_gamma;
+    q.w_rows = q.v5 ? (size_t)n_nu * ec_row_words(n_gamma)
+               : q.prefix ? ((n_seg * 3 * kMomStride + p.n_pairs / 2 + 2 + 1) & ~(size_t)1) : 0;
+    q.w_gt = 5 * (size_t)n_gamma;
+    q.w_ang = kAngCols * (size_t)p.n_pairs;
+    q.w_raw = kRawCols * (size_t)p.n_pairs;
+    q.w_part = q.prefix ? 0 : (size_t)n_nu * p.S * p.W();
+    return q;
 }
 
-size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi) {
-    EcPlan a = ec_plan(variant, n_mu, n_phi, AGNPY_INTEG_LOGLOG);  // J=1 -> largest S
-    EcPlan b = ec_plan(variant, n_mu, n_phi, AGNPY_INTEG_TRAPZ);
-    size_t per = ec_words(a, n_nu, n_gamma);
-    size_t per_b = ec_words(b, n_nu, n_gamma);
-    return (per > per_b ? per : per_b) * sizeof(double) * (size_t)n_models + 256;
+size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi, int integ) {
+    return ec_path(variant, n_nu, n_gamma, n_mu, n_phi, integ).words() * sizeof(double) * (size_t)n_models + 256;
 }
 
 template <int INTEG, int J>
@@ -1271,42 +1319,23 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
            int n_nu, const double* gamma, int n_gamma, const double* mu, int n_mu,
            const double* phi, int n_phi, const double* ne_table, int integ, double* sed,
            double* ws, cudaStream_t stream) {
-    const bool fold_req = (integ & AGNPY_INTEG_FOLD_PHI) != 0 && getenv("AGNPY_B200_EC_NOFOLD") == nullptr;
-    integ &= ~AGNPY_INTEG_FOLD_PHI;
-    const bool prefix = integ == AGNPY_INTEG_TRAPZ_PREFIX;
-    if (prefix) integ = AGNPY_INTEG_TRAPZ;  // same tables (trapz weights folded into wf)
-    EcPlan p = ec_plan(variant, n_mu, n_phi, integ);
-    // mirror-symmetric phi grid (the caller vouches for it): one table entry per mirror pair, if
-    // the folded (mu, phi) table still feeds the polynomial kernel
-    if (fold_req && n_phi >= 2 &&
-        (variant == AGNPY_EC_ISO_MONO || variant == AGNPY_EC_SS_DISK || variant == AGNPY_EC_BLR)) {
-        EcPlan pf = ec_plan(variant, n_mu, (n_phi + 1) / 2, integ);
-        // np.trapz: only where the folded table still feeds the polynomial kernel (the small-table
-        // kernel does not carry the partner bookkeeping); trapz_loglog and the prefix path: always
-        if (prefix || integ == AGNPY_INTEG_LOGLOG || pf.n_pairs >= 512) p = pf;
-    }
-    const bool use_v4 = getenv("AGNPY_B200_EC_V4") != nullptr;  // A/B knob: 4-instruction body
-    if (use_v4 && p.J == 5) {  // the small-table kernel is instantiated for 1, 2, 4 and 8 pairs per thread
-        p.J = 4;
-        p.S = (p.n_pairs + p.T * p.J - 1) / (p.T * p.J);
-    }
-    // the polynomial path pays off once a (nu, model) has a few hundred pairs; the ring / point
-    // source variants (<= n_phi pairs) stay on the v4 kernel
-    const bool v5 = integ == AGNPY_INTEG_TRAPZ && !prefix && !use_v4 && p.n_pairs >= 512;
+    const EcPath q = ec_path(variant, n_nu, n_gamma, n_mu, n_phi, integ);
+    const EcPlan p = q.p;
+    const bool prefix = q.prefix, v5 = q.v5, fused_ag = q.fused_ag;
+    integ = q.integ;
     const size_t M = (size_t)n_models;
-    // carve: {A,G} table first (16-byte aligned: ws comes from cudaMalloc), then the rest
+    // carve (every area has an even word count except the last ones: nt and rows stay 16-byte aligned,
+    // ws comes from cudaMalloc)
     double2* nt = (double2*)ws;
-    double* rows = (double*)(nt + M * n_nu * n_gamma);  // 16-byte aligned: even word counts
-    double* gt = rows + M * std::max((size_t)n_nu * ec_row_words(n_gamma),
-                                     (size_t)((p.n_pairs + kPairSeg - 1) / kPairSeg) * 3 * kMomStride +
-                                         p.n_pairs / 2 + 2);
-    double* ang = gt + M * 5 * n_gamma;
-    double* raw = ang + M * kAngCols * p.n_pairs;
-    double* part = raw + M * kRawCols * p.n_pairs;
-    int* hull = (int*)(part + M * n_nu * p.S * p.W());
+    double* rows = ws + M * q.w_nt;
+    double* gt = rows + M * q.w_rows;
+    double* ang = gt + M * q.w_gt;
+    double* raw = ang + M * q.w_ang;
+    double* part = raw + M * q.w_raw;
+    int* hull = (int*)(part + M * q.w_part);
     {
         int nB = (p.n_pairs + 127) / 128, nC = (n_gamma + 127) / 128;
-        dim3 grid(1 + nB + ((v5 || prefix) ? 0 : nC * n_nu), n_models);
+        dim3 grid(1 + nB + ((v5 || prefix || fused_ag) ? 0 : nC * n_nu), n_models);
         ec_tables_kernel<<<grid, 128, 0, stream>>>(variant, models, ne_kind, nu, n_nu, gamma, n_gamma,
                                                    mu, n_mu, phi, n_phi, ne_table, integ, p.n_pairs,
                                                    gt, hull, raw, nt);
@@ -1418,8 +1447,9 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
     }
     dim3 grid(Sg, n_nu, n_models);
     timing_begin(stream);
+    const double2* nt_arg = fused_ag ? nullptr : nt;
 #define EC_LAUNCH(I, JJ) launch_main<I, JJ>(grid, p.T, smem, stream, models, nu, n_nu, gt, hull, \
-                                            n_gamma, iters, nt, ang, p.n_pairs, p.S, part)
+                                            n_gamma, iters, nt_arg, ang, p.n_pairs, p.S, part)
     if (integ == AGNPY_INTEG_LOGLOG) EC_LAUNCH(AGNPY_INTEG_LOGLOG, 1);
     else if (p.J == 8) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 8);
     else if (p.J == 4) EC_LAUNCH(AGNPY_INTEG_TRAPZ, 4);

@@ -23,7 +23,7 @@ int launch_ssc(const agnpy_model_t* models, int n_models, const double* nu, int 
                int n_seed, int integ, double* out, double* scratch, cudaStream_t stream);
 
 // bytes of scratch the EC / tau pipelines need for `n_models` models
-size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi);
+size_t ec_workspace_bytes(int variant, int n_models, int n_nu, int n_gamma, int n_mu, int n_phi, int integ);
 int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, const double* nu,
            int n_nu, const double* gamma, int n_gamma, const double* mu, int n_mu,
            const double* phi, int n_phi, const double* ne_table, int integ, double* sed,

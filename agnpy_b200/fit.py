@@ -95,6 +95,9 @@ def scenario_of(targets):
     return "ec_" + "_".join(x for x in ("blr", "dt") if x in t)
 
 
+_HOST_CHUNK = 4096   # parameter vectors per host -> device hand-over of a large batch
+
+
 def build_models(pars, d_L, ne_kind, scenario):
     """flat fit parameter vectors [B, n_par] -> dict of MODEL_DTYPE arrays per component.
     `d_L` (cm; scalar or one per vector) may be None: it is then derived from each vector's z as the
@@ -216,26 +219,31 @@ class FitSedBatch:
             d_L = np.broadcast_to(np.asarray(d_L, dtype=np.float64), (B,))
 
         def local(idx):
-            # only this rank's shard of the parameter table is turned into model rows
+            # only this rank's shard of the parameter table is turned into model rows, _HOST_CHUNK
+            # vectors at a time: the kernel launches are asynchronous, so the host prepares the rows
+            # of the next chunk (log10 scalings, d_L(z), ...) while the device works on this one
             lo, hi = int(idx[0]), int(idx[-1]) + 1
-            models = build_models(pars[lo:hi], None if d_L is None else d_L[lo:hi], self.ne_kind,
-                                  self.scenario)
             n = hi - lo
             if self._total is None or self._total.shape[0] < n:
                 self._total = self.torch.empty(n, self.n_nu, dtype=self.torch.float64,
                                                device=self.device)
+            for a in range(lo, hi, _HOST_CHUNK):
+                b = min(a + _HOST_CHUNK, hi)
+                models = build_models(pars[a:b], None if d_L is None else d_L[a:b], self.ne_kind,
+                                      self.scenario)
+                total = self._total[a - lo:b - lo]
+                for k, (name, plan) in enumerate(self.plans.items()):
+                    part = plan._local(models[name])
+                    total.copy_(part) if k == 0 else total.add_(part)
+                if self.ebl is not None:
+                    z_dev = self.torch.from_numpy(np.ascontiguousarray(models["synch"]["z"])).to(self.device)
+                    t, nu_dev = self.ebl, self.plans["synch"].nu
+                    st = self.torch.cuda.current_stream(self.device).cuda_stream
+                    _lib.check(_lib.lib().agnpy_b200_ebl_absorption(
+                        b - a, z_dev.data_ptr(), nu_dev.data_ptr(), self.n_nu, t["e"].data_ptr(),
+                        t["e"].numel(), t["z"].data_ptr(), t["z"].numel(), t["v"].data_ptr(), 1,
+                        total.data_ptr(), st), "agnpy_b200_ebl_absorption")
             total = self._total[:n]
-            for k, (name, plan) in enumerate(self.plans.items()):
-                part = plan._local(models[name])
-                total.copy_(part) if k == 0 else total.add_(part)
-            if self.ebl is not None:
-                z_dev = self.torch.from_numpy(np.ascontiguousarray(models["synch"]["z"])).to(self.device)
-                t, nu_dev = self.ebl, self.plans["synch"].nu
-                st = self.torch.cuda.current_stream(self.device).cuda_stream
-                _lib.check(_lib.lib().agnpy_b200_ebl_absorption(
-                    n, z_dev.data_ptr(), nu_dev.data_ptr(), self.n_nu, t["e"].data_ptr(),
-                    t["e"].numel(), t["z"].data_ptr(), t["z"].numel(), t["v"].data_ptr(), 1,
-                    total.data_ptr(), st), "agnpy_b200_ebl_absorption")
             return total
         return local
 

@@ -50,3 +50,19 @@ if rank == 0:
                       "extrapolated_65536_models_s": 65536 / (B / float(t.item()))}), flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
+
+# optional: where the time of one rank goes (python scripts/time_c5.py 16384 trapz breakdown)
+if len(sys.argv) > 3 and sys.argv[3] == "breakdown" and world == 1:
+    from agnpy_b200.fit import build_models
+    t0 = time.perf_counter()
+    models = build_models(pars, None, "BrokenPowerLaw", "ec_blr_dt")
+    host_s = time.perf_counter() - t0
+    parts = {"host build_models (d_L from z)": host_s * 1e3}
+    for name, plan in model.plans.items():
+        plan._local(models[name]); torch.cuda.synchronize()   # warm-up at full size (buffers)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); e0.record(); plan._local(models[name]); e1.record(); torch.cuda.synchronize()
+        parts[name] = e0.elapsed_time(e1)
+        parts[name + " (wall)"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); out = model(pars, copy=False); parts["whole call, copy=False (wall)"] = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"breakdown_ms": parts, "models": B}), flush=True)
