@@ -4,12 +4,15 @@ The product path has no CPU fallback: if the shared library is missing, or there
 CUDA device, calls raise.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libagnpy_b200.so"
+if os.environ.get("AGNPY_B200_CHECKED") == "1":   # debugging build with index checks in the kernels
+    LIB_PATH = _PKG / "libagnpy_b200_checked.so"
 
 # constants of include/agnpy_b200.h
 NE_POWERLAW, NE_BROKEN_POWERLAW, NE_LOG_PARABOLA = 0, 1, 2

@@ -7,6 +7,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libagnpy_b200.so"
+LIB_CHECKED = PKG / "libagnpy_b200_checked.so"   # -DAGNPY_B200_CHECKS: index checks in the kernels
 SOURCES = ["runtime.cu", "synch_ssc.cu", "ec.cu", "tau.cu", "bb.cu", "targets.cu", "integrate.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -31,10 +32,14 @@ def needs_build():
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, checked=False):
+    """checked=True builds the variant with the kernels' AGB_CHECK index checks compiled in (a debugging
+    aid, loaded instead of the product library when AGNPY_B200_CHECKED=1)"""
+    if not checked and not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    target = LIB_CHECKED if checked else LIB
+    flags = NVCC_FLAGS + (["-DAGNPY_B200_CHECKS"] if checked else [])
+    cmd = [_nvcc(), *flags, "-o", str(target)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -44,9 +49,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libagnpy_b200.so")
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, checked="--checked" in sys.argv))

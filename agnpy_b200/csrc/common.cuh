@@ -10,6 +10,25 @@
 #include <stdint.h>
 #include "../../include/agnpy_b200.h"
 
+// Bounds / invariant checks of the kernels' index arithmetic.  Compiled in only with -DAGNPY_B200_CHECKS
+// (`python agnpy_b200/build.py --checked` -> libagnpy_b200_checked.so, selected at run time by
+// AGNPY_B200_CHECKED=1); a failed check prints its location and traps, which the host sees as a CUDA
+// error.  compute-sanitizer is not available on the measurement pool: the GPU test-suite run against the
+// checked build (profiles/r2_checked_build.txt) stands in for memcheck on the shared-memory indexing.
+#ifdef AGNPY_B200_CHECKS
+#include <stdio.h>
+#define AGB_CHECK(cond)                                                                          \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            printf("AGB_CHECK failed: %s  (%s:%d, block %d,%d,%d thread %d)\n", #cond, __FILE__, \
+                   __LINE__, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);                   \
+            __trap();                                                                            \
+        }                                                                                        \
+    } while (0)
+#else
+#define AGB_CHECK(cond) ((void)0)
+#endif
+
 namespace agb {
 
 // ---- constants: astropy>=7 (CODATA 2018) in CGS; literals are the repr() of the doubles the

@@ -216,7 +216,10 @@ __device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ ra
     }
     if (t < cnt) {
         if (keys) keys[j0 + t] = v;
-        else ec_pair_store(raw, n_pairs, row, (int)(~(unsigned)(v & 0xffffffffull)), j0 + t);
+        else {
+            AGB_CHECK((int)(~(unsigned)(v & 0xffffffffull)) >= 0 && (int)(~(unsigned)(v & 0xffffffffull)) < n_pairs);
+            ec_pair_store(raw, n_pairs, row, (int)(~(unsigned)(v & 0xffffffffull)), j0 + t);
+        }
     }
 }
 
@@ -243,6 +246,8 @@ __global__ void __launch_bounds__(256) ec_pairs_merge_kernel(const double* __res
         }
         rank += lo;
     }
+    AGB_CHECK(rank >= 0 && rank < n_pairs);
+    AGB_CHECK((int)(~(unsigned)(key & 0xffffffffull)) >= 0 && (int)(~(unsigned)(key & 0xffffffffull)) < n_pairs);
     ec_pair_store(r, n_pairs, ang + (size_t)m * kAngCols * n_pairs, (int)(~(unsigned)(key & 0xffffffffull)), rank);
 }
 
@@ -502,6 +507,7 @@ __global__ void __launch_bounds__(256) ec_main_kernel(
                 }
             }
             lo[jj] = k;
+            AGB_CHECK(k >= 0 && k <= n_gamma);
             if (cj > 0.0) { kmin = min(kmin, k); kmax = max(kmax, k); }
         }
         double thread_sum = 0.0;
@@ -768,6 +774,7 @@ __device__ __forceinline__ int ec_warp_first_le(const long long* __restrict__ s_
     while (len > 0) {
         const int s = (len + 31) >> 5;
         const int k = lo + lane * s;
+        AGB_CHECK(lo >= 0 && lo + len <= n);
         const bool gt = k < lo + len && s_Gi[k] > c;
         const int cnt = __popc(__ballot_sync(0xffffffffu, gt));
         if (cnt == 0) return lo;
@@ -880,6 +887,7 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
             // (G descending: a prefix count, on high words; a tie there is inside the guard band), and
             // the guard band itself: an entry within 3 units of the high word of c (>= 1.4e-6
             // relative) next to the index -> decide that pair with the reference's own formula
+            AGB_CHECK(wlo >= 0 && wlo <= whi && whi <= n_gamma);
             int lo[J];
             unsigned near[J];  // min over the entries of (high word of c) - (high word of G_k) + 3, unsigned
             unsigned doubt = always_doubt;
@@ -945,6 +953,9 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
             }
             kbeg = max(kbeg, klo);
             kmid = min(max(kmid, kbeg), khi + 1);
+            AGB_CHECK(kbeg >= 0 && kmid >= 0 && kmid <= khi + 1 && khi < n_gamma);  // kbeg > kmid: empty ranges
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) AGB_CHECK(lo[jj] >= 0 && lo[jj] <= n_gamma);
             // the b-independent suffix sum at each pair's own first unmasked index seeds its accumulator
             // (both are exactly 0 past the last electron index): the loads are in flight during phase 1
             double acc[J];
@@ -962,6 +973,7 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
             // four gamma steps per trip and no remainder loop: the row carries kRowPad zero entries
             // after the last index, so running past khi adds exact zeros
             for (int k = kmid; k <= khi; k += 4) {
+                AGB_CHECK(k >= 0 && k + 3 < n_gamma + kRowPad);
                 const double2 q0 = s_QR[k], q1 = s_QR[k + 1], q2 = s_QR[k + 2], q3 = s_QR[k + 3];
 #define EC_STEP(q)                                                                        \
     _Pragma("unroll") for (int jj = 0; jj < J; ++jj) acc[jj] = fma(q.x, b2[jj], acc[jj]); \
@@ -974,6 +986,7 @@ __global__ void __launch_bounds__(T, MINB) ec_main_poly_kernel(
             for (int jj = 0; jj < J; ++jj) thread_sum = fma(W[jj], acc[jj], thread_sum);
             thread_sum += fold_corr;
         }
+        AGB_CHECK(r >= 0 && r < L_nu);
         s_sum[(size_t)r * (T + 1) + tid] = thread_sum;
     }
     // per warp: sum its 32 columns of every frequency row.  Lane l takes row l % 8 (+8, +16, ...),
@@ -1174,6 +1187,7 @@ __global__ void __launch_bounds__(256) ec_moment_kernel(
                     if (h[mid] > hG + 3) lo = mid + 1; else hi = mid;
                 }
                 const double* ms = mm + (size_t)seg * 3 * kMomStride;
+                AGB_CHECK(lo >= 0 && lo <= cnt && cnt <= kPairSeg);
                 M0 += ms[lo];
                 M1 += ms[kMomStride + lo];
                 M2 += ms[2 * kMomStride + lo];

@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(32 * kSscLogWarps) ssc_loglog_kernel(
             g_last = gl;
         }
         double acc[2] = {0.0, 0.0};
+        AGB_CHECK(g_first >= 0 && g_last < n_groups);
         for (int g = g_first; g <= g_last; ++g) {
             const int k = g * 31 + lane;
             const bool in = k < n_gamma;
@@ -577,6 +578,7 @@ __global__ void __launch_bounds__(256) ssc_trapz_kernel(
         // every lane evaluates every seed of the warp's band (a warp pays for the instruction
         // whether or not a lane is predicated off); a lane outside its own band adds with weight 0.
         // F stays finite there (h2 = 0 or a finite q), so 0 * F = 0 exactly.
+        AGB_CHECK(JB < JA || (JA >= 0 && JB < n_seed));
         const double2* pq = s_q + JA;
         const double* pw = s_w + JA;
         // t in [ja - JA, jb - JA]  <=>  (unsigned)(t - rel_lo) <= rel_n;  empty band: never true

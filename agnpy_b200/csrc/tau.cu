@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(256) tau_main_kernel(
             part[((size_t)m * n_nu + i0 + threadIdx.x) * S + slice] = 0.0;
         return;
     }
+    AGB_CHECK(live >= 0 && live <= n_t);
     const int t_end = min(live, (slice + 1) * kTauSlice);
     for (int t = slice * kTauSlice + threadIdx.x; t < t_end; t += blockDim.x) {
         // the weight first: a warp of retired (folded phi axis) or weightless entries costs one
