@@ -1,6 +1,6 @@
 """Short runs of every kernel family for ncu (round 2): EC-BLR direct + prefix (config 2, 64 models),
 EC-BLR / SSC / synchrotron trapz_loglog, SSC / synchrotron np.trapz (config 1), tau_blr (config 3)."""
-import sys
+import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
@@ -11,7 +11,8 @@ from tests import cases
 
 torch.cuda.set_device(0)
 g = bench.grids()
-ec_models = bench.synthetic_models(64)
+N_MODELS = int(os.environ.get("PROFILE_MODELS", "64"))   # 256 = the batch of the bench step
+ec_models = bench.synthetic_models(N_MODELS)
 for integ in ("trapz", "trapz_prefix", "trapz_loglog"):
     plan = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"], phi=g["phi"],
                     integrator=integ)
@@ -19,7 +20,7 @@ for integ in ("trapz", "trapz_prefix", "trapz_loglog"):
     print("ec_blr", integ, out.shape, float(np.nanmax(out)))
 rng = np.random.default_rng(1)
 c1 = cases.case_c1()
-n = 64
+n = N_MODELS
 models = _lib.make_models(n)
 for i in range(n):
     _core.model_row(models, i, z=c1["z"], d_L=c1["d_L"], delta_D=rng.uniform(5, 30), mu_s=1.0,

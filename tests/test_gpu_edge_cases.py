@@ -257,7 +257,7 @@ def test_ec_poly_frequency_chunks(monkeypatch, l_nu, order):
 @pytest.mark.parametrize("n_mu,n_phi", [(16, 32), (17, 32), (31, 17), (70, 31), (130, 67)])
 def test_ec_poly_pair_counts(monkeypatch, n_mu, n_phi):
     """pair counts around the plan switches: 512 (v4 kernel below, polynomial path from there on),
-    one partly filled 1024-pair sort segment, several segments, J = 4 and J = 8 tiles"""
+    one partly filled 1024-pair sort segment, several segments, tiles of 4 and of 5 pairs per thread"""
     monkeypatch.setenv("AGNPY_B200_EC_LNU", "4")
     c = cases.case_c2(n_nu=9, r=2e17, n_gamma=90, n_mu=n_mu, n_phi=n_phi)
     assert_parity(blr_call(c), cases.ORACLE_EC["blr"](c), what=f"{n_mu}x{n_phi} pairs")
@@ -276,6 +276,41 @@ def test_ec_poly_long_gamma_grid(monkeypatch):
     monkeypatch.setenv("AGNPY_B200_EC_LNU", "8")
     c = cases.case_c2(n_nu=5, r=5e17, n_gamma=1000, n_mu=24, n_phi=24)
     assert_parity(blr_call(c), cases.ORACLE_EC["blr"](c), what="n_gamma = 1000")
+
+
+@pytest.mark.parametrize("integrator", ["trapz", "trapz_prefix", "trapz_loglog"])
+def test_repeated_launches_are_bit_identical(integrator):
+    """the kernels synchronise through mbarriers, shuffles, ballots and shared-memory hand-overs and
+    are written to be deterministic (fixed reduction orders, no atomics on the data path): 25 launches
+    of the same batch -- enough to fill the GPU several times over, so that blocks are scheduled
+    differently from launch to launch -- must agree to the last bit (a shared-memory race or a missing
+    barrier shows up as run-to-run noise; compute-sanitizer racecheck is not available on the pool)"""
+    import torch
+    from agnpy_b200.batch import SedBatch
+    import bench
+    g = bench.grids()
+    n = 8 if integrator == "trapz_loglog" else 48
+    models = bench.synthetic_models(n)
+    plan = SedBatch("ec_blr", g["nu"], "BrokenPowerLaw", gamma=g["gamma"], mu=g["mu"], phi=g["phi"],
+                    integrator=integrator)
+    first = plan(models)
+    assert np.all(np.isfinite(first)) and first.max() > 0
+    for _ in range(25 if integrator != "trapz_loglog" else 6):
+        np.testing.assert_array_equal(plan(models), first)
+    c1 = cases.case_c1()
+    ssc_models = _lib.make_models(64)
+    rng = np.random.default_rng(3)
+    from agnpy_b200 import _core
+    for i in range(64):
+        _core.model_row(ssc_models, i, z=c1["z"], d_L=c1["d_L"], delta_D=rng.uniform(5, 30), mu_s=1.0,
+                        B=10 ** rng.uniform(-1.5, 0.5), R_b=10 ** rng.uniform(15.5, 16.5),
+                        ne=[10 ** rng.uniform(-9, -7), rng.uniform(1.5, 2.5), rng.uniform(2.6, 4),
+                            10 ** rng.uniform(3.5, 5), 10.0, 1e6, 0, 0])
+    ssc = SedBatch("ssc", c1["nu"], "BrokenPowerLaw", gamma=c1["gamma"],
+                   integrator="trapz" if integrator == "trapz_prefix" else integrator)
+    first = ssc(ssc_models)
+    for _ in range(25):
+        np.testing.assert_array_equal(ssc(ssc_models), first)
 
 
 # ---- the np.trapz SSC path: gamma slots, seed grids that are not log-uniform ----------------------
