@@ -313,8 +313,8 @@ __device__ __forceinline__ void ec_nu_role(const agnpy_model_t& M, const double*
 // First table launch (128 threads); the block role follows from blockIdx.x:
 //   [0, 1)                     gamma tables + hull
 //   [1, 1 + nB)                unsorted pair values, 128 pairs per block
-//   [1 + nB, 1 + nB + nC*n_nu) {A, G} table, 128 gammas of one frequency per block (not launched
-//                              on the np.trapz path, whose row role computes A and G itself)
+//   [1 + nB, 1 + nB + nC*n_nu) {A, G} table, 128 gammas of one frequency per block: trapz_loglog only
+//                              (the np.trapz paths form A and G in their row role / main kernel)
 __global__ void __launch_bounds__(128) ec_tables_kernel(
     int variant, const agnpy_model_t* __restrict__ models, int ne_kind,
     const double* __restrict__ nu, int n_nu, const double* __restrict__ gamma, int n_gamma,
@@ -738,7 +738,7 @@ __device__ __forceinline__ long long warp_min_ll(long long v) {
 // ---------------------------------------------------------------------------------------------
 // ec_main_poly_kernel<J, T>: grid = (S pair slices, nu chunks, models), T threads x J consecutive pairs
 // of the globally c-sorted table (so the first unmasked indices of a warp lie within a few entries
-// of each other).  A block keeps its pairs in registers and walks the L_nu <= 8 frequencies of its
+// of each other).  A block keeps its pairs in registers and walks the L_nu frequencies of its
 // chunk; their rows arrive by TMA bulk copies (cp.async.bulk + one mbarrier per row) and the warps
 // run through the chunk independently, no block barrier after the prologue.  Per (warp, nu):
 //   * index window [wlo, whi] = first entries with G_k <= the warp's largest / smallest threshold,
@@ -756,16 +756,18 @@ __device__ __forceinline__ long long warp_min_ll(long long v) {
 //     pair weights live in registers, dead pairs carry W = b = 0 and need no special casing;
 //   * the partial sums of the chunk's frequencies are parked in shared memory and reduced once per
 //     block (8 values per lane + 2 shuffles) instead of once per frequency.
-// Why it looks like this (ncu, profiles/r1f_* -> r2*_ec_main_poly_full.txt): a non-FP64 instruction
+// Why it looks like this (ncu, profiles/r1f_* -> r2_final_kernels_full.txt): a non-FP64 instruction
 // costs the sub-partition a dispatch slot the DFMA stream cannot use (scripts/micro/fp64_mix.cu), and
 // round 1 executed 1500 instructions per (warp, nu) for 800 DFMAs, 545 of them outside the gamma
-// loop with 48 % of the stall samples.  Now: 1320 instructions for 784 DFMAs (global sort of the
-// pair table: windows of ~2 instead of ~5 entries, 11 instead of 39 wasted DFMAs in the ragged
-// start), 96 registers -> 5 blocks per SM; FP64 pipe 57 % -> 66 % active.  Tried and measured slower
-// (profiles/r2_tune_ec.txt): 8 pairs per thread (64 x 8 ties, 128 x 8 loses: wider windows), a
-// second accumulator chain per pair, 8 gamma steps per trip, and a ring of row buffers with
-// full / empty mbarriers feeding 25-200 frequencies per block (the prologue it amortises is
-// latency other blocks already hide; uneven chunks cost more).
+// loop with 48 % of the stall samples.  Round 2: global sort of the pair table (windows of ~2 instead
+// of ~5 entries, 11 instead of 39 wasted DFMAs in the ragged start), the passes above, suffix sums as
+// accumulator seeds, and 5 pairs per thread at 128 registers / 4 blocks per SM (40 DFMAs for 8 other
+// instructions per trip): FP64 pipe 57 % -> 68.5 % active, 2.545 -> 2.056 ms per 256 models.  Tried
+// and measured slower (profiles/r2_tune_ec.txt): 8 and 10 pairs per thread, a second accumulator
+// chain per pair, 8 gamma steps per trip, blocks of 160-256 threads with more frequencies each, 6
+// blocks per SM at 80 registers, and a ring of row buffers with full / empty mbarriers feeding 25-200
+// frequencies per block (the prologue it amortises is latency other blocks already hide; uneven
+// chunks cost more).
 // ---------------------------------------------------------------------------------------------
 // first k in [0, n] with G_k <= c (G descending), all lanes cooperating: 32 probes per round
 __device__ __forceinline__ int ec_warp_first_le(const long long* __restrict__ s_Gi, int n, long long c,
