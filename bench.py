@@ -39,6 +39,9 @@ MODELS_PER_GPU = 256
 N_NU, N_GAMMA, N_MU, N_PHI = 200, 200, 100, 50
 FLOPS_PER_POINT = 16          # nominal FP64 ops per compton_kernel point (np.trapz)
 EXEC_FLOPS_PER_POINT = 4      # executed: 2 DFMA per visited point (polynomial form, FMA = 2)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch of 256 models, from the
+# ncu --set full capture summarised in profiles/r2_final_kernels_full.txt (reported as roofline.traffic)
+NCU_DRAM_BYTES_PER_LAUNCH = 358936576
 METRIC = "SED evals/sec (EC-BLR)"
 UNIT = "SED/s"
 WORKLOAD = ("configs[1]: ExternalCompton on SphericalShellBLR (Lyalpha), 200 nu x 200 gamma x "
@@ -530,7 +533,7 @@ def run_cuda(args):
         "roofline": {
             "bound": "fp64", "kernel": "ec_main_poly_kernel<5,128> (128 threads x 5 sorted pairs, 128 registers, 4 blocks/SM)",
             "achieved": executed, "peak": peak / 1e12, "unit": "TFLOP/s",
-            "frac": executed / (peak / 1e12), "traffic": None,
+            "frac": executed / (peak / 1e12), "traffic": NCU_DRAM_BYTES_PER_LAUNCH if MODELS_PER_GPU == 256 else None,
             "what": "EXECUTED FP64 work of the dominant kernel: 2 DFMA (4 flop) per visited integrand "
                     "point x visited points per launch / CUDA-event time of that launch, over the "
                     "measured DFMA-chain peak of this GPU",
@@ -549,8 +552,11 @@ def run_cuda(args):
                         "all (gamma,nu)-only / (mu,phi)-only factors are hoisted into tables (2 DFMA "
                         "per point: wf K = P + Q b^2 + R b), points the reference masks to exactly 0 "
                         "are skipped and mirror pairs of the symmetric phi grid share one evaluation"},
-            "traffic_note": "DRAM traffic is not measurable in-run; ncu: profiles/r2_all_kernels_full.txt "
-                            "(~1.7 % of HBM peak: the path is FP64-pipe bound)"},
+            "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full "
+                            "capture of this kernel at this batch size (profiles/r2_final_kernels_full.txt), "
+                            "not measured in this run; algorithmic in/out is 0.45 MB, the rest is the 328 MB of "
+                            "polynomial rows written by ec_tables2_kernel and read once per pair slice "
+                            "(1.7 % of HBM peak: the kernel is FP64-pipe bound)"},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                          "sample": f"{n_cpu} SED(s) of the same workload, nu-chunked by 25, 1 thread "
                                    "(the reference is single-threaded)",
