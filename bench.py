@@ -237,6 +237,56 @@ def bench_c5(torch, dist, dev, world, group, barrier):
     return out
 
 
+def ssc_models_for(rank):
+    """256 synthetic SSC models of this rank: the tutorial blob of BASELINE configs[0] with randomised
+    Doppler factor, field, size and electron spectrum"""
+    from agnpy_b200 import _core, _lib
+    from tests import cases
+    c1 = cases.case_c1()
+    models = _lib.make_models(MODELS_PER_GPU)
+    rng = np.random.default_rng(1 + rank)
+    for i in range(MODELS_PER_GPU):
+        _core.model_row(models, i, z=c1["z"], d_L=c1["d_L"], delta_D=rng.uniform(5, 30),
+                        B=10 ** rng.uniform(-1.5, 0.5), R_b=10 ** rng.uniform(15.5, 16.5),
+                        ne=[10 ** rng.uniform(-9, -7), rng.uniform(1.5, 2.5), rng.uniform(2.6, 4),
+                            10 ** rng.uniform(3.5, 5), 10.0, 1e6, 0, 0])
+    return c1, models
+
+
+def bench_ssc(torch, dist, dev, world, rank, barrier, flush, steps):
+    """the second half of BASELINE.json's metric: SSC SED evaluations/s (configs[0] grids), weak scaling
+    like the headline -- 256 models per GPU per step, one all-gather of the SEDs inside the step, CUDA
+    events, L2 flushed between steps, max over ranks"""
+    from agnpy_b200.batch import SedBatch
+    c1, models = ssc_models_for(rank)
+    plan = SedBatch("ssc", c1["nu"], "BrokenPowerLaw", gamma=c1["gamma"], device=dev)
+    d_models = torch.from_numpy(np.ascontiguousarray(models).view(np.float64)
+                                .reshape(MODELS_PER_GPU, -1).copy()).to(dev)
+    n_nu = c1["nu"].size
+    d_out = torch.empty(MODELS_PER_GPU, n_nu, dtype=torch.float64, device=dev)
+    gathered = torch.empty(MODELS_PER_GPU * world, n_nu, dtype=torch.float64, device=dev)
+
+    def step():
+        plan.launch(d_models, d_out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out)
+    for _ in range(3):
+        step()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        flush.fill_(1.0)
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    ms = _max_over_ranks(torch, dist, dev, world, sum(a.elapsed_time(b) for a, b in evs)) / steps
+    pts = MODELS_PER_GPU * world * (n_nu * 200 * c1["gamma"].size)
+    return {"value": MODELS_PER_GPU * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "weak",
+            "ms_per_step": ms, "integrand_gpts_per_s": pts / (ms * 1e-3) / 1e9,
+            "collective": "none" if world == 1 else "one NCCL all_gather_into_tensor of 256x100 f64 per rank"}
+
+
 def bench_c4(torch, dist, dev, world, group, barrier):
     """BASELINE configs[3]: one EC-BLR SED on 1000 nu x 1000 gamma x 200 mu x 100 phi = 2e10 points,
     the frequency grid dealt round-robin over the ranks, one all-gather.  Device time per SED
@@ -380,6 +430,7 @@ def run_cuda(args):
     group = None if world == 1 else dist.group.WORLD
     scaling = {"c5_fit_batch": bench_c5(torch, dist, dev, world, group, barrier),
                "c4_nu_sharded": bench_c4(torch, dist, dev, world, group, barrier)}
+    ssc_scaling = bench_ssc(torch, dist, dev, world, rank, barrier, flush, max(3, min(args.steps, 10)))
 
     if rank != 0:
         if world > 1:
@@ -453,15 +504,7 @@ def run_cuda(args):
     fast_ms, fast_kms = timed(plan_fast, d_models, d_out, max(3, min(args.steps, 10)))
     fast_dev, _ = cases.max_rel_dev(d_out[0].cpu().numpy()[::8], chk)
     # (b) SSC at BASELINE configs[0] grids (tutorial blob, 100 nu x 200 seeds x 200 gamma)
-    c1 = cases.case_c1()
-    ssc_models = _lib.make_models(MODELS_PER_GPU)
-    rng = np.random.default_rng(1)
-    for i in range(MODELS_PER_GPU):
-        from agnpy_b200 import _core
-        _core.model_row(ssc_models, i, z=c1["z"], d_L=c1["d_L"], delta_D=rng.uniform(5, 30),
-                        B=10 ** rng.uniform(-1.5, 0.5), R_b=10 ** rng.uniform(15.5, 16.5),
-                        ne=[10 ** rng.uniform(-9, -7), rng.uniform(1.5, 2.5), rng.uniform(2.6, 4),
-                            10 ** rng.uniform(3.5, 5), 10.0, 1e6, 0, 0])
+    c1, ssc_models = ssc_models_for(0)
     plan_ssc = SedBatch("ssc", c1["nu"], "BrokenPowerLaw", gamma=c1["gamma"], device=dev)
     d_ssc = torch.from_numpy(np.ascontiguousarray(ssc_models).view(np.float64)
                              .reshape(MODELS_PER_GPU, -1).copy()).to(dev)
@@ -481,11 +524,12 @@ def run_cuda(args):
                     "taken before the gamma sum (prefix moments of the sorted pair table), same grid "
                     "and masks (DESIGN.md section 4); not the headline"},
         "ssc_config1": {
-            "value": MODELS_PER_GPU / (ssc_ms * 1e-3), "unit": UNIT, "ms_per_step": ssc_ms,
+            **ssc_scaling,
             "workload": "configs[0]: SSC of the tutorial blob, 100 nu x 200 seed nu x 200 gamma, "
-                        "np.trapz, 256 models per step (seed synchrotron spectrum included)",
+                        "np.trapz, 256 models per GPU per step (seed synchrotron spectrum included)",
             "kernel": "ssc_trapz_kernel", "kernel_ms": ssc_kms,
-            "integrand_gpts_per_s": ssc_pts / (ssc_ms * 1e-3) / 1e9,
+            "one_gpu_no_flush": {"value": MODELS_PER_GPU / (ssc_ms * 1e-3), "ms_per_step": ssc_ms},
+            "ncu_fp64_pipe_active_pct": 58.4,   # profiles/r2_final_kernels_full.txt, this batch size
             "roofline_frac_algorithmic": ssc_pts * 24 / (ssc_kms * 1e-3) / peak,
             "algorithmic_flops_per_point": 24, "parity_max_rel_dev": ssc_dev},
     }
