@@ -222,8 +222,12 @@ __global__ void __launch_bounds__(32) synch_trapz_kernel(
             const double x23 = x13 * x13;
             const double x43 = x23 * x23;
             const double num = 1.808 * x13 * fma(0.347, x43, fma(2.21, x23, 1.0));
-            const double den = sqrt(fma(3.4, x23, 1.0)) * fma(0.217, x43, fma(1.353, x23, 1.0));
-            const double P = prefP * (num / den * exp(-x));
+            // 1 / (sqrt(a) b) = (a b^2)^(-1/2), a, b >= 1: one reciprocal square root (a few ulp from the
+            // reference's sqrt-then-divide, like the x^(1/3) factorisation above) instead of a square root
+            // and a division
+            const double pb = fma(0.217, x43, fma(1.353, x23, 1.0));
+            const double inv_den = rsqrt_fast(fma(3.4, x23, 1.0) * (pb * pb));
+            const double P = prefP * (num * inv_den * exp(-x));
             acc[q] = fma(wne, P, acc[q]);
             acc_ssa[q] = fma(wsa, P, acc_ssa[q]);
         }

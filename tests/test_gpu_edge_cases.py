@@ -278,6 +278,20 @@ def test_ec_poly_long_gamma_grid(monkeypatch):
     assert_parity(blr_call(c), cases.ORACLE_EC["blr"](c), what="n_gamma = 1000")
 
 
+@pytest.mark.parametrize("plan", ["128,5", "128,4", "64,8", "128,8"])
+def test_ec_poly_tile_shapes_agree(monkeypatch, plan):
+    """every instantiated tile shape of the polynomial kernel (threads x pairs per thread; the default is
+    chosen by padding, the others stay reachable through AGNPY_B200_EC_PLAN for tuning) gives the oracle's
+    result, and the shapes agree with each other to rounding (the pair order inside a thread differs)"""
+    c = cases.case_c2(n_nu=23, r=2e17, n_gamma=130, n_mu=60, n_phi=44)       # 1320 folded pairs
+    monkeypatch.delenv("AGNPY_B200_EC_PLAN", raising=False)
+    default = blr_call(c)
+    monkeypatch.setenv("AGNPY_B200_EC_PLAN", plan)
+    got = blr_call(c)
+    assert_parity(got, cases.ORACLE_EC["blr"](c), what=f"plan {plan}")
+    assert_parity(got, default, rtol=1e-13, what=f"plan {plan} vs default")
+
+
 @pytest.mark.parametrize("integrator", ["trapz", "trapz_prefix", "trapz_loglog"])
 def test_repeated_launches_are_bit_identical(integrator):
     """the kernels synchronise through mbarriers, shuffles, ballots and shared-memory hand-overs and
