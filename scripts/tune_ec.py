@@ -1,7 +1,8 @@
 """Development aid: time the EC-BLR np.trapz main kernel under the A/B knobs of ec.cu
-(AGNPY_B200_EC_PLAN="T,J", AGNPY_B200_EC_LNU, AGNPY_B200_EC_NOFOLD; earlier sweeps, with knobs that
-have since been removed, are kept in profiles/r2_tune_ec.txt).
-Usage: python scripts/tune_ec.py ["V6=1 PLAN=128,4" "PLAN=64,8 LNU=4" ...]   (default: a built-in sweep)
+(AGNPY_B200_EC_PLAN="T,J" with T,J in {128,5 128,4 64,8 128,8}, AGNPY_B200_EC_LNU, AGNPY_B200_EC_NOFOLD;
+earlier sweeps, with knobs and tile shapes that have since been removed, are kept in
+profiles/r2_tune_ec.txt).
+Usage: python scripts/tune_ec.py ["PLAN=128,4" "PLAN=64,8 LNU=4" ...]   (default: a built-in sweep)
 Prints, per variant: wall per step and main-kernel time for 256 models, SED/s, and the largest
 deviation from the first variant (all variants must agree to rounding)."""
 import os, sys
@@ -14,7 +15,7 @@ from agnpy_b200.batch import SedBatch
 
 torch.cuda.set_device(0)
 g = bench.grids()
-KNOBS = ("PLAN", "LNU", "NOFOLD", "MINB6")
+KNOBS = ("PLAN", "LNU", "NOFOLD")
 
 
 def run(n_models, reps=8):
@@ -37,7 +38,7 @@ def run(n_models, reps=8):
     return e0.elapsed_time(e1) / reps, kms / max(kn, 1), d_out.cpu().numpy()
 
 
-variants = sys.argv[1:] or ["PLAN=128,4", "PLAN=64,8", "PLAN=64,4", "PLAN=128,8", "PLAN=128,4 LNU=4", "PLAN=128,4 NOFOLD=1"]
+variants = sys.argv[1:] or ["PLAN=128,5", "PLAN=128,4", "PLAN=64,8", "PLAN=128,8", "PLAN=128,5 LNU=4", "PLAN=128,5 NOFOLD=1"]
 ref = None
 for v in variants:
     for k in KNOBS:
