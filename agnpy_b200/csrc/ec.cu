@@ -17,11 +17,12 @@
 // (kernels.py:36-40) whenever c lies within a guard band of a table entry.
 //
 // Map of this file:
-//   ec_tables_kernel / ec_tables2_kernel   gamma table, pair table (sorted by c, optionally with
+//   ec_tables_kernel / ec_tables2_kernel / ec_rows_merge_kernel
+//                                          gamma table, pair table (sorted by c, optionally with
 //                                          the phi axis folded), {A,G} table, polynomial rows
 //   ec_main_poly_kernel<J,T>               np.trapz, >= 512 pairs: 2 DFMA per point (the default)
 //   ec_main_kernel<INTEG,J>                trapz_loglog, and np.trapz with few pairs (4 instr/pt)
-//   ec_prefix_kernel                       opt-in: np.trapz through suffix sums over gamma
+//   ec_moments_kernel / ec_moment_kernel   opt-in: np.trapz through prefix moments of the pair table
 //   ec_finish_kernel                       fixed-order sum of the warp partials x prefactor
 //   run_ec                                 plan, scratch carving, launches
 #include <limits.h>
@@ -186,7 +187,7 @@ __device__ __forceinline__ void ec_pair_store(const double* __restrict__ raw, in
     row[6 * n_pairs + j] = raw[4 * n_pairs + src];
 }
 // `keys` == nullptr (one segment): the sorted rows are written directly; else the sorted keys of
-// this segment are stored for ec_pairs_merge_kernel, which interleaves the segments.
+// this segment are stored for the merge role of ec_rows_merge_kernel, which interleaves the segments.
 __device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ raw, int n_pairs,
                                                    double* __restrict__ row,
                                                    unsigned long long* __restrict__ keys, int seg,
@@ -227,9 +228,8 @@ __device__ __forceinline__ void ec_pairs_sort_role(const double* __restrict__ ra
 // plus the number of larger keys in every other segment (keys are unique), found by binary search.
 // A globally sorted table halves the spread of first-unmasked indices inside a warp of the main
 // kernel (a 1024-pair segment covers the whole range of thresholds, 1/n_seg of the table does not).
-__global__ void __launch_bounds__(256) ec_pairs_merge_kernel(const double* __restrict__ raw, int n_pairs,
-                                                             int n_seg, double* __restrict__ ang) {
-    const int m = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void ec_pairs_merge_role(const double* __restrict__ raw, int n_pairs, int n_seg,
+                                                    double* __restrict__ ang, int m, int j) {
     if (j >= n_pairs) return;
     const double* r = raw + (size_t)m * kRawCols * n_pairs;
     const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(r + 5 * (size_t)n_pairs);
@@ -588,9 +588,9 @@ __host__ __device__ __forceinline__ int ec_row_words(int n_gamma) {
     return (2 * (n_gamma + kRowPad) + 2 * n_gamma + 2 + 1) & ~1;
 }
 
-// Second table launch (1024 threads); the block role follows from blockIdx.x:
-//   [0, nSeg)            pair table: one sorted segment per block (from the unsorted values)
-//   [nSeg, nSeg + nR)    np.trapz path only: polynomial rows, one warp per (nu, model) row.
+// Polynomial rows of the np.trapz path, one warp per (nu, model) row (they depend on the gamma table
+// only, so they share the third table launch with the merge of the sorted pair segments, see
+// ec_rows_merge_kernel).
 // Row role: lane l owns gamma indices l, l+32, ...: it evaluates y, A, G (kernels.py:61-65 in the
 // operation order of ec_nu_role), writes {Q,R} and G, and the warp builds the suffix sums of
 // P = wf A from the top of the grid down (shuffle scan per group of 32 plus a running carry).
@@ -659,23 +659,35 @@ __device__ __forceinline__ void ec_poly_row_role(
     }
 }
 
-__global__ void __launch_bounds__(kTab2Threads) ec_tables2_kernel(
+// Second table launch (1024 threads): one sorted segment of the pair table per block (from the unsorted
+// values).
+__global__ void __launch_bounds__(kTab2Threads) ec_tables2_kernel(const double* __restrict__ raw, int n_pairs,
+                                                                  int n_seg, double* __restrict__ ang) {
+    __shared__ unsigned long long s_x[kPairSeg];
+    const int m = blockIdx.y;
+    const double* r = raw + (size_t)m * kRawCols * n_pairs;
+    // raw column 5 holds the keys; const_cast: it is scratch of this launch sequence
+    unsigned long long* keys = n_seg > 1
+        ? reinterpret_cast<unsigned long long*>(const_cast<double*>(r) + 5 * (size_t)n_pairs) : nullptr;
+    ec_pairs_sort_role(r, n_pairs, ang + (size_t)m * kAngCols * n_pairs, keys, blockIdx.x, s_x);
+}
+
+// Third table launch (256 threads); the block role follows from blockIdx.x:
+//   [0, n_rb)             np.trapz polynomial path: rows, 8 per block (one warp each); first in the
+//                         grid: they run longest
+//   [n_rb, n_rb + n_mb)   more than one sorted segment: global rank of every pair (merge)
+constexpr int kRowWarps = 8;
+__global__ void __launch_bounds__(32 * kRowWarps) ec_rows_merge_kernel(
     const double* __restrict__ raw, int n_pairs, int n_seg, double* __restrict__ ang,
     const agnpy_model_t* __restrict__ models, const double* __restrict__ nu, int n_nu,
     const double* __restrict__ gamma, int n_gamma, const double* __restrict__ gt,
-    const int* __restrict__ hull, double* __restrict__ rows) {
-    __shared__ unsigned long long s_x[kPairSeg];
+    const int* __restrict__ hull, double* __restrict__ rows, int n_rb) {
     const int m = blockIdx.y;
-    if ((int)blockIdx.x < n_seg) {
-        const double* r = raw + (size_t)m * kRawCols * n_pairs;
-        // raw column 5 holds the keys; const_cast: it is scratch of this launch sequence
-        unsigned long long* keys = n_seg > 1
-            ? reinterpret_cast<unsigned long long*>(const_cast<double*>(r) + 5 * (size_t)n_pairs) : nullptr;
-        ec_pairs_sort_role(r, n_pairs, ang + (size_t)m * kAngCols * n_pairs, keys, blockIdx.x, s_x);
-    } else {
+    if ((int)blockIdx.x < n_rb)
         ec_poly_row_role(models, nu, n_nu, gamma, n_gamma, gt, hull, rows,
-                         ((int)blockIdx.x - n_seg) * (kTab2Threads / 32) + (threadIdx.x >> 5), m);
-    }
+                         (int)blockIdx.x * kRowWarps + (threadIdx.x >> 5), m);
+    else
+        ec_pairs_merge_role(raw, n_pairs, n_seg, ang, m, ((int)blockIdx.x - n_rb) * (int)blockDim.x + threadIdx.x);
 }
 
 // 1-D bulk copy (TMA engine) global -> shared, completion counted on an mbarrier
@@ -1356,16 +1368,18 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
                                                    mu, n_mu, phi, n_phi, ne_table, integ, p.n_pairs,
                                                    gt, hull, raw, nt);
         note_launch();
-        // sorted pair table (+ the polynomial rows of the np.trapz path)
+        // sorted segments of the pair table
         const int n_seg = (p.n_pairs + kPairSeg - 1) / kPairSeg;
-        const int n_rb = v5 ? (n_nu + kTab2Threads / 32 - 1) / (kTab2Threads / 32) : 0;
-        dim3 grid2(n_seg + n_rb, n_models);
-        ec_tables2_kernel<<<grid2, kTab2Threads, 0, stream>>>(raw, p.n_pairs, n_seg, ang, models, nu,
-                                                              n_nu, gamma, n_gamma, gt, hull, rows);
+        dim3 grid2(n_seg, n_models);
+        ec_tables2_kernel<<<grid2, kTab2Threads, 0, stream>>>(raw, p.n_pairs, n_seg, ang);
         note_launch();
-        if (n_seg > 1) {  // interleave the sorted segments into one globally sorted table
-            dim3 grid3((p.n_pairs + 255) / 256, n_models);
-            ec_pairs_merge_kernel<<<grid3, 256, 0, stream>>>(raw, p.n_pairs, n_seg, ang);
+        // polynomial rows of the np.trapz path + (more than one segment) the global pair order
+        const int n_rb = v5 ? (n_nu + kRowWarps - 1) / kRowWarps : 0;
+        const int n_mb = n_seg > 1 ? (p.n_pairs + 32 * kRowWarps - 1) / (32 * kRowWarps) : 0;
+        if (n_rb + n_mb > 0) {
+            dim3 grid3(n_rb + n_mb, n_models);
+            ec_rows_merge_kernel<<<grid3, 32 * kRowWarps, 0, stream>>>(raw, p.n_pairs, n_seg, ang, models, nu,
+                                                                       n_nu, gamma, n_gamma, gt, hull, rows, n_rb);
             note_launch();
         }
     }
