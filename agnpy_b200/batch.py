@@ -13,6 +13,8 @@ blocks are joined with ONE NCCL all-gather (every model is independent: no other
 Grids live on the device for the life of the plan; per call the model table is copied
 host->device from pinned memory and the result device->host into pinned memory.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -68,6 +70,9 @@ class GatherBuffers:
         if need_out and self.out is None:
             self.out = torch.empty(world * rows, cols, dtype=torch.float64, device=device)
         return self.block, self.out
+
+
+HOST_GATHER_TIMEOUT_S = float(os.environ.get("AGNPY_B200_HOST_GATHER_TIMEOUT_S", "600"))
 
 
 class HostGather:
@@ -140,8 +145,16 @@ class HostGather:
         self.seq += 1
         self.flags[8 * self.rank] = self.seq
         others = self.flags[::8]
+        spins, t0 = 0, None
         while int(others.min()) < self.seq:
-            pass
+            spins += 1
+            if spins & 0xffff == 0:      # a rank that died must not leave the others spinning for ever
+                import time
+                t0 = t0 or time.monotonic()
+                if time.monotonic() - t0 > HOST_GATHER_TIMEOUT_S:
+                    late = [r for r in range(self.world) if int(others[r]) < self.seq]
+                    raise RuntimeError(f"gather='host': ranks {late} did not deliver their shard of call "
+                                       f"{self.seq} within {HOST_GATHER_TIMEOUT_S} s")
 
     def close(self):
         try:
