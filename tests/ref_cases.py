@@ -286,6 +286,104 @@ def _ec_ps(side, A, idx):
 
 
 # ------------------------------------------------------------------------------------------
+# random parameter sweep: every process of 8(a) on 8 random blobs / targets / electron spectra at small
+# grids (the BASELINE cases above fix the physical parameters; this one moves all of them)
+# ------------------------------------------------------------------------------------------
+SWEEP_KINDS = ("PowerLaw", "BrokenPowerLaw", "LogParabola", "ExpCutoffPowerLaw", "ExpCutoffBrokenPowerLaw")
+
+
+def _sweep_draw(seed):
+    rng = np.random.default_rng(4200 + seed)
+    kind = SWEEP_KINDS[seed % len(SWEEP_KINDS)]
+    gmin, gmax = 10 ** rng.uniform(0.5, 2), 10 ** rng.uniform(5, 7.5)
+    k = 10 ** rng.uniform(-9, -5)
+    ne_args = {
+        "PowerLaw": (k, rng.uniform(1.8, 3), gmin, gmax),
+        "BrokenPowerLaw": (k, rng.uniform(1.5, 2.5), rng.uniform(2.6, 4), 10 ** rng.uniform(3, 4.5), gmin, gmax),
+        "LogParabola": (k, rng.uniform(1.8, 2.6), rng.uniform(0.05, 0.6), 10 ** rng.uniform(2.5, 4), gmin, gmax),
+        "ExpCutoffPowerLaw": (k, rng.uniform(1.5, 2.8), 10 ** rng.uniform(4, 6), gmin, gmax),
+        "ExpCutoffBrokenPowerLaw": (k, rng.uniform(1.5, 2.4), rng.uniform(2.6, 3.8), 10 ** rng.uniform(4.5, 6),
+                                    10 ** rng.uniform(3, 4), gmin, gmax),
+    }[kind]
+    M_BH = 10 ** rng.uniform(8, 9.5) * 1.988409870698051e33
+    R_g = orc.G_NEWTON * M_BH / orc.C_LIGHT**2
+    L_disk = 10 ** rng.uniform(45, 46.7)
+    return dict(
+        ne_kind=kind, ne_args=ne_args, z=rng.uniform(0.05, 2.5), d_L=10 ** rng.uniform(27, 28.7),
+        delta_D=rng.uniform(3, 45), mu_s=rng.uniform(0.3, 0.99995), B=10 ** rng.uniform(-2, 1),
+        R_b=10 ** rng.uniform(15, 17), L_disk=L_disk, xi_line=rng.uniform(0.01, 0.3),
+        epsilon_line=cases.EPS_LINE * rng.uniform(0.5, 2), R_line=10 ** rng.uniform(16.5, 17.5),
+        xi_dt=rng.uniform(0.05, 0.6), epsilon_dt=cases.EPS_DT * rng.uniform(0.5, 2),
+        R_dt=10 ** rng.uniform(18, 19), r=10 ** rng.uniform(16, 19.5), M_BH=M_BH, eta=rng.uniform(0.05, 0.2),
+        R_in=6 * R_g, R_out=rng.uniform(100, 500) * R_g,
+        nu=np.logspace(rng.uniform(9, 12), rng.uniform(26, 29), 12), nu_tau=np.logspace(24, 29, 10),
+        gamma=np.logspace(np.log10(gmin) - 0.3, np.log10(gmax) + 0.2, 70),
+        gamma_ec=np.logspace(0.5, 8.5, 80), mu=np.linspace(-1, 1, 18), phi=np.linspace(0, 2 * np.pi, 14))
+
+
+@case("random_sweep", rtol=RTOL_EXP_TAIL)
+def _random_sweep(side, A, idx):
+    out = []
+    for seed in range(8):
+        c = _sweep_draw(seed)
+        blob = (c["z"], c["d_L"], c["delta_D"])
+        if side == "orc":
+            ne = (c["ne_kind"], c["ne_args"])
+            out += [
+                orc.synch_sed_flux(c["nu"], *blob, c["B"], c["R_b"], *ne, gamma=c["gamma"].copy()),
+                orc.ssc_sed_flux(c["nu"], *blob, c["B"], c["R_b"], *ne, gamma=c["gamma"].copy()),
+                orc.ssc_sed_flux(c["nu"], *blob, c["B"], c["R_b"], *ne, integrator="trapz_loglog",
+                                 gamma=c["gamma"].copy()),
+                orc.ec_blr_sed_flux(c["nu"], *blob, c["mu_s"], c["R_b"], c["L_disk"], c["xi_line"],
+                                    c["epsilon_line"], c["R_line"], c["r"], *ne, gamma=c["gamma_ec"].copy(),
+                                    mu=c["mu"], phi=c["phi"]),
+                orc.ec_blr_sed_flux(c["nu"], *blob, c["mu_s"], c["R_b"], c["L_disk"], c["xi_line"],
+                                    c["epsilon_line"], c["R_line"], c["r"], *ne, integrator="trapz_loglog",
+                                    gamma=c["gamma_ec"].copy(), mu=c["mu"], phi=c["phi"]),
+                orc.ec_dt_sed_flux(c["nu"], *blob, c["mu_s"], c["R_b"], c["L_disk"], c["xi_dt"],
+                                   c["epsilon_dt"], c["R_dt"], c["r"], *ne, gamma=c["gamma_ec"].copy(),
+                                   phi=c["phi"]),
+                orc.ec_ss_disk_sed_flux(c["nu"], *blob, c["mu_s"], c["R_b"], c["M_BH"], c["L_disk"], c["eta"],
+                                        c["R_in"], c["R_out"], c["r"], *ne, gamma=c["gamma_ec"].copy(),
+                                        mu_size=16, phi=c["phi"]),
+                orc.tau_blr(c["nu_tau"], c["z"], 1.0, c["L_disk"], c["xi_line"],
+                            c["epsilon_line"], c["R_line"], c["r"], l_size=20, mu=c["mu"], phi=c["phi"])
+                if seed % 2 == 0 else
+                orc.tau_blr_mu_s(c["nu_tau"], c["z"], c["mu_s"], c["L_disk"], c["xi_line"], c["epsilon_line"],
+                                 c["R_line"], c["r"], u_size=20, mu=c["mu"], phi=c["phi"]),
+                orc.tau_dt(c["nu_tau"], c["z"], 1.0, c["L_disk"], c["xi_dt"], c["epsilon_dt"], c["R_dt"], c["r"],
+                           l_size=20, phi=c["phi"]),
+            ]
+            continue
+        Q = A.Q
+        S, SSC, EC, Ab = A.agnpy.Synchrotron, A.agnpy.SynchrotronSelfCompton, A.agnpy.ExternalCompton, A.agnpy.Absorption
+        bq = (c["z"], Q(c["d_L"], "cm"), c["delta_D"])
+        ne = _ne_q(A, c)
+        nu, nut = Q(c["nu"], "Hz"), Q(c["nu_tau"], "Hz")
+        ecb = (nu, *bq, c["mu_s"], Q(c["R_b"], "cm"))
+        blr = (Q(c["L_disk"], "erg s-1"), c["xi_line"], c["epsilon_line"], Q(c["R_line"], "cm"), Q(c["r"], "cm"))
+        dt = (Q(c["L_disk"], "erg s-1"), c["xi_dt"], c["epsilon_dt"], Q(c["R_dt"], "cm"), Q(c["r"], "cm"))
+        out += [
+            _val(S.evaluate_sed_flux(nu, *bq, Q(c["B"], "G"), Q(c["R_b"], "cm"), *ne, gamma=c["gamma"].copy())),
+            _val(SSC.evaluate_sed_flux(nu, *bq, Q(c["B"], "G"), Q(c["R_b"], "cm"), *ne, gamma=c["gamma"].copy())),
+            _val(SSC.evaluate_sed_flux(nu, *bq, Q(c["B"], "G"), Q(c["R_b"], "cm"), *ne,
+                                       integrator=A.integ("trapz_loglog"), gamma=c["gamma"].copy())),
+            _val(EC.evaluate_sed_flux_blr(*ecb, *blr, *ne, gamma=c["gamma_ec"].copy(), mu=c["mu"], phi=c["phi"])),
+            _val(EC.evaluate_sed_flux_blr(*ecb, *blr, *ne, integrator=A.integ("trapz_loglog"),
+                                          gamma=c["gamma_ec"].copy(), mu=c["mu"], phi=c["phi"])),
+            _val(EC.evaluate_sed_flux_dt(*ecb, *dt, *ne, gamma=c["gamma_ec"].copy(), phi=c["phi"])),
+            _val(EC.evaluate_sed_flux_ss_disk(*ecb, Q(c["M_BH"], "g"), Q(c["L_disk"], "erg s-1"), c["eta"],
+                                              Q(c["R_in"], "cm"), Q(c["R_out"], "cm"), Q(c["r"], "cm"), *ne,
+                                              gamma=c["gamma_ec"].copy(), mu_size=16, phi=c["phi"])),
+            _val(Ab.evaluate_tau_blr(nut, c["z"], 1.0, *blr, l_size=20, mu=c["mu"], phi=c["phi"]))
+            if seed % 2 == 0 else
+            _val(Ab.evaluate_tau_blr_mu_s(nut, c["z"], c["mu_s"], *blr, u_size=20, mu=c["mu"], phi=c["phi"])),
+            _val(Ab.evaluate_tau_dt(nut, c["z"], 1.0, *dt, l_size=20, phi=c["phi"])),
+        ]
+    return np.concatenate([np.ravel(x) for x in out])
+
+
+# ------------------------------------------------------------------------------------------
 # config 3: gamma-gamma opacities (docs/snippets/absorption_snippet.py:13-29) and the rest of tau()
 # ------------------------------------------------------------------------------------------
 def _tau(side, A, idx, which, mu_s=1.0, r=None, n_nu=200):
