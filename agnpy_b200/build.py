@@ -24,10 +24,10 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not LIB.exists():
+def needs_build(target=LIB):
+    if not target.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = target.stat().st_mtime
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "agnpy_b200.h"]
     return any(p.stat().st_mtime > t for p in deps)
 
@@ -35,9 +35,9 @@ def needs_build():
 def build(force=False, verbose=False, checked=False):
     """checked=True builds the variant with the kernels' AGB_CHECK index checks compiled in (a debugging
     aid, loaded instead of the product library when AGNPY_B200_CHECKED=1)"""
-    if not checked and not force and not needs_build():
-        return LIB
     target = LIB_CHECKED if checked else LIB
+    if not force and not needs_build(target):
+        return target
     flags = NVCC_FLAGS + (["-DAGNPY_B200_CHECKS"] if checked else [])
     cmd = [_nvcc(), *flags, "-o", str(target)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
