@@ -1446,8 +1446,8 @@ int run_ec(int variant, const agnpy_model_t* models, int n_models, int ne_kind, 
         }
         const size_t row_bytes = (size_t)row_words * sizeof(double);
         // shared memory per frequency: the row, its parked partial sums and its barrier; blocks per SM
-        // as the register budget allows (5 x 128 threads at 96 registers, 3 at 8 pairs per thread; 6 of
-        // 64 threads x 8 pairs, 8 of 64 x 4)
+        // as the register budget allows (128 threads: 4 at 5 pairs per thread / 128 registers, 5 at 4 pairs /
+        // 96 registers, 3 at 8 pairs; 64 threads x 8 pairs: 6)
         const size_t per_nu = row_bytes + 8 + (size_t)(p.T + 1) * sizeof(double);
         const int blocks_per_sm = p.T >= 128 ? (p.J == 8 ? 3 : p.J == 5 ? 4 : 5) : 6;
         const size_t smem_cap = (size_t)(227 * 1024) / blocks_per_sm - 1024;
