@@ -9,7 +9,7 @@ is sharded over ranks (weak scaling) and the SED blocks are joined by one NCCL a
 inside the timed step.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # CUDA arm
-  python bench.py --impl reference [...]                       # CPU arm: oracle port, all cores
+  python bench.py --impl reference [...]                       # CPU arm: the unmodified reference, all cores
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
 ranks); `e2e` goes through the public host-buffer API (pinned H2D of the model table, D2H of
@@ -17,9 +17,10 @@ the SEDs, wall clock); `roofline` is for the dominant kernel (ec_main_poly_kerne
 EXECUTED FP64 work over the measured DFMA peak, the nominal 16 flop/point figure of SURVEY 8(a) is
 kept beside it as `algorithmic`; `cpu_baseline` is the reference's own code (agnpy v0.5.0 from
 baseline/_ref, on the miniature astropy of oracle/astropy_stub) on one core of this box, or the
-oracle port where the reference install did not travel.  `extra` carries, at every N, the two
-strong-scaling workloads of BASELINE.json: configs[4] (65 536 fit parameter vectors in total) and
-configs[3] (one 2e10-point SED, frequency-sharded).
+oracle port where the reference install did not travel.  `extra` carries, at every N, the second
+half of BASELINE.json's metric -- SSC SED evaluations/s at configs[0], measured as a weak-scaling step
+like the headline -- and the two strong-scaling workloads: configs[4] (65 536 fit parameter vectors
+in total) and configs[3] (one 2e10-point SED, frequency-sharded).
 """
 import argparse
 import json
