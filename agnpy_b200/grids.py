@@ -25,11 +25,11 @@ def trapz_prefix(*args, **kwargs):
         "agnpy_b200.trapz_prefix only selects the device integrator; it is not a host function")
 
 
-def trapz_loglog(y, x, axis=-1, intervals=False):
+def trapz_loglog(y, x, axis=0, intervals=False):
     """Log-log trapezoidal rule of the reference, agnpy/utils/math.py:55-119: each interval is
     integrated as the power law through its end points; intervals with a zero end point or a repeated
-    abscissa contribute 0.  Same signature as the reference's function (`intervals=True` returns the
-    per-interval integrals instead of their sum).  Quantities keep their units (y.unit * x.unit).
+    abscissa contribute 0.  Same signature and default axis (0) as the reference's function
+    (`intervals=True` returns the per-interval integrals instead of their sum).  Quantities keep their units (y.unit * x.unit).
 
     Two roles: passed as `integrator=` to any evaluate_* it selects the fused device-side rule
     (AGNPY_INTEG_LOGLOG); called directly it integrates `y` along `axis` on the GPU through
@@ -41,7 +41,13 @@ def trapz_loglog(y, x, axis=-1, intervals=False):
     yv = np.asarray(getattr(y, "value", y), dtype=np.float64)
     xv = np.asarray(getattr(x, "value", x), dtype=np.float64)
     if xv.ndim != 1:
-        raise ValueError("x must be one-dimensional (the reference slices it along `axis` too)")
+        # the reference also takes x already reshaped for broadcasting against y (axes_reshaper):
+        # every axis but `axis` of length 1
+        if xv.ndim == yv.ndim and xv.size == xv.shape[axis]:
+            xv = xv.reshape(-1)
+        else:
+            raise ValueError("x must be one-dimensional, or shaped like y with length 1 on every axis "
+                             "but `axis`")
     if yv.shape[axis] != xv.size:
         raise ValueError(f"y has {yv.shape[axis]} samples along axis {axis}, x has {xv.size}")
     moved = np.ascontiguousarray(np.moveaxis(yv, axis, -1))

@@ -350,3 +350,43 @@ def test_boundary_accepts_ndarray_subclass_quantities():
         strip(1.0 * au.cm, "Hz", "nu")
     import agnpy_b200.units as bu
     assert bu.HAVE_ASTROPY is False          # the stand-in is never mistaken for astropy by the product
+
+
+def test_reference_import_paths_and_host_helpers():
+    """the reference's import paths work on the drop-in (`agnpy.emission_regions`, `agnpy.utils.math`,
+    `agnpy.utils.conversion`), and the small host helpers agree with the reference's own functions"""
+    from agnpy_b200.emission_regions import Blob
+    from agnpy_b200.utils import conversion as conv, math as umath
+    assert Blob is ab.Blob and umath.trapz_loglog is ab.trapz_loglog
+    assert umath.gamma_e_to_integrate is ab.gamma_e_to_integrate
+    import inspect
+    assert inspect.signature(umath.trapz_loglog).parameters["axis"].default == 0     # utils/math.py:55
+    a, b, c = umath.axes_reshaper(np.arange(3.0), np.arange(4.0), np.arange(5.0))
+    assert (a.shape, b.shape, c.shape) == ((3, 1, 1), (1, 4, 1), (1, 1, 5))
+    x = np.array([0.0, -2.0, 1e-320, 1.0, 1e300, np.inf])
+    assert np.all(np.isfinite(umath.log(x))) and umath.log(x)[3] == 0.0
+    assert conv.nu_to_epsilon_prime(1e20 * u.Hz, z=1, delta_D=10) == pytest.approx(
+        2 * 6.62607015e-27 * 1e20 / (9.1093837015e-28 * 2.99792458e10**2) / 10, rel=1e-15)
+    assert strip(conv.B_to_cgs(2 * u.G), "G") == 2.0
+    assert conv.to_R_g_units(1e16 * u.cm, 1e9 * u.M_sun) == pytest.approx(67.7219994400538, rel=1e-12)
+    assert strip(conv.mec2, "erg") == pytest.approx(8.1871057769e-7, rel=1e-10)
+    from oracle import reference_loader
+    if not reference_loader.available():
+        return
+    reference_loader.load()
+    import importlib
+    ref_math = importlib.import_module("agnpy.utils.math")
+    ref_conv = importlib.import_module("agnpy.utils.conversion")
+    import astropy.units as au
+    for got, want in zip(umath.axes_reshaper(np.arange(3.0), np.arange(4.0)),
+                         ref_math.axes_reshaper(np.arange(3.0), np.arange(4.0))):
+        np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(umath.log(x), ref_math.log(x))
+    for p in (1.0, 2.5):
+        assert umath.power_law_integral(2.0, p, 10.0, 1e3) == ref_math.power_law_integral(2.0, p, 10.0, 1e3)
+    nu = np.logspace(10, 28, 7)
+    np.testing.assert_allclose(conv.nu_to_epsilon_prime(nu * u.Hz, z=0.5, delta_D=20),
+                               np.asarray(ref_conv.nu_to_epsilon_prime(nu * au.Hz, z=0.5, delta_D=20)), rtol=1e-15)
+    np.testing.assert_allclose(conv.to_R_g_units(1e16 * u.cm, 1e9 * u.M_sun),
+                               float(ref_conv.to_R_g_units(1e16 * au.cm, 1e9 * au.M_sun)), rtol=1e-15)
+    assert umath.ftiny == ref_math.ftiny and umath.fmax == ref_math.fmax
