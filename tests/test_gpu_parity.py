@@ -488,3 +488,19 @@ def test_trapz_loglog_callable():
     np.testing.assert_allclose(per_interval.sum(axis=0), ab.trapz_loglog(y, xg, axis=0), rtol=1e-12)
     q = ab.trapz_loglog(y[:, 0, 0] * u.Unit("erg cm-3"), xg * u.cm, axis=0)
     assert q.value == pytest.approx(float(ab.trapz_loglog(y[:, 0, 0], xg, axis=0)))
+
+
+def test_trapz_loglog_callable_reference_call_shapes():
+    """the way the reference's own callers use it: default axis (0) and an x already reshaped by
+    axes_reshaper to broadcast against y (utils/math.py:88-92)"""
+    from agnpy_b200.utils.math import axes_reshaper, trapz_loglog
+    rng = np.random.default_rng(5)
+    gamma, nu = np.logspace(1, 6, 50), np.logspace(10, 20, 7)
+    _gamma, _nu = axes_reshaper(gamma, nu)
+    y = _gamma**-2.2 * (1 + _nu / 1e15) ** -0.5 * rng.uniform(0.5, 2.0, (50, 7))
+    want = ab.trapz_loglog(y, gamma, axis=0)
+    np.testing.assert_array_equal(trapz_loglog(y, gamma), want)          # default axis
+    np.testing.assert_array_equal(trapz_loglog(y, _gamma), want)         # reshaped x
+    np.testing.assert_array_equal(trapz_loglog(y, _gamma, axis=0), want)
+    with pytest.raises(ValueError):
+        trapz_loglog(y, np.broadcast_to(_gamma, y.shape))                # a full-shaped x is not supported
