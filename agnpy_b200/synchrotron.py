@@ -4,8 +4,11 @@ fused FP64 CUDA kernel K1."""
 import numpy as np
 
 from . import _core, _lib, spectra
+from . import constants as const
 from .grids import as_grid, gamma_e_to_integrate, integrator_code, np_trapz
 from .units import strip, wrap
+
+B_CR = 4.414e13   # critical magnetic field in G (synchrotron.py:13), delta approximation only
 
 __all__ = ["Synchrotron", "ProtonSynchrotron"]
 
@@ -73,6 +76,29 @@ class Synchrotron:
         return self.evaluate_sed_flux(nu, b.z, b.d_L, b.delta_D, b.B, b.R_b, b.n_e,
                                       *b.n_e.parameters, ssa=self.ssa,
                                       integrator=self.integrator, gamma=b.gamma_e)
+
+    @staticmethod
+    def evaluate_sed_flux_delta_approx(nu, z, d_L, delta_D, B, R_b, n_e, *args):
+        """delta-function approximation of the synchrotron SED, Dermer & Menon (2009) eq. 7.70
+        (synchrotron.py:213-227): a closed form per frequency -- no integral, hence host arithmetic:
+        each frequency maps to one Lorentz factor gamma_s = sqrt(eps' B_cr / B), and the SED is
+        delta_D^4 c sigma_T U_B gamma_s^3 V_b n_e(gamma_s) / (6 pi d_L^2)."""
+        nu_hz = strip(nu, "Hz", "nu")
+        d_L, B, R_b = strip(d_L, "cm", "d_L"), strip(B, "G", "B"), strip(R_b, "cm", "R_b")
+        eps = (1 + z) * (const.h * nu_hz / const.mec2) / delta_D
+        gamma_s = np.sqrt(eps / (B / B_CR))
+        n = n_e.evaluate(gamma_s, *args)
+        n = strip(n, "cm-3", "n_e") if hasattr(n, "to_value") else np.asarray(n, dtype=np.float64)
+        V_b = 4 / 3 * np.pi * R_b**3
+        U_B = B**2 / (8 * np.pi)
+        pref = delta_D**4 * const.c * const.sigma_T * U_B / (6 * np.pi * d_L**2)
+        return wrap(pref * gamma_s**3 * (V_b * n), "erg cm-2 s-1")
+
+    def sed_flux_delta_approx(self, nu):
+        """synchrotron.py:246-258"""
+        b = self.blob
+        return self.evaluate_sed_flux_delta_approx(nu, b.z, b.d_L, b.delta_D, b.B, b.R_b, b.n_e,
+                                                   *b.n_e.parameters)
 
     def sed_luminosity(self, nu):
         """synchrotron.py:259-265"""

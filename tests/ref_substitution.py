@@ -1,0 +1,72 @@
+"""pytest plugin: run the REFERENCE'S OWN test files with the CUDA classes substituted.
+
+    python -m pytest -p tests.ref_substitution <reference>/agnpy/synchrotron/tests/test_synchrotron.py ...
+
+The unmodified reference is imported (oracle/reference_loader.py: baseline/_ref or /root/reference, on the
+miniature astropy of the test infrastructure) and the compute classes of the hot path are replaced in its
+package namespaces before the reference's test modules are collected:
+
+    agnpy.synchrotron.Synchrotron, .ProtonSynchrotron  -> agnpy_b200.Synchrotron, .ProtonSynchrotron
+    agnpy.compton.SynchrotronSelfCompton, .ExternalCompton -> agnpy_b200....
+    agnpy.absorption.Absorption                          -> agnpy_b200.Absorption
+
+Everything else the tests touch stays the reference's own: Blob, the spectra classes and their
+normalisation class methods, the targets, the literature data files, the comparison utilities -- the scenario
+of INTEGRATION.md, where a maintainer keeps the package and swaps the numpy bodies for the C ABI.
+Test infrastructure: used by tests/test_reference_suite_on_cuda.py (gpu)."""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from oracle import reference_loader  # noqa: E402
+
+SUBSTITUTED = {
+    "agnpy.synchrotron": ("Synchrotron", "ProtonSynchrotron"),
+    "agnpy.compton": ("SynchrotronSelfCompton", "ExternalCompton"),
+    "agnpy.absorption": ("Absorption",),
+}
+# the module files that define the classes inside those packages
+_INNER = {
+    "Synchrotron": "agnpy.synchrotron.synchrotron", "ProtonSynchrotron": "agnpy.synchrotron.proton_synchrotron",
+    "SynchrotronSelfCompton": "agnpy.compton.synchrotron_self_compton",
+    "ExternalCompton": "agnpy.compton.external_compton", "Absorption": "agnpy.absorption.targets_absorption",
+}
+
+
+def substitute():
+    import importlib
+
+    import agnpy_b200 as ab
+    import agnpy_b200.units as bu
+    agnpy = reference_loader.load()
+    # results leave the package as Quantities of the units module the caller uses: the astropy branch of
+    # the boundary (agnpy_b200/units.py: wrap), here on the astropy the reference was imported with
+    import astropy.units as au
+    bu._astropy_units, bu.HAVE_ASTROPY = au, True
+    done = []
+    for pkg, names in SUBSTITUTED.items():
+        mod = importlib.import_module(pkg)
+        for name in names:
+            cuda_cls = getattr(ab, name)
+            for target in (mod, agnpy, importlib.import_module(_INNER[name])):
+                if hasattr(target, name):
+                    setattr(target, name, cuda_cls)
+            done.append(f"{pkg}.{name}")
+    return done
+
+
+def pytest_configure(config):
+    done = substitute()
+    config._agnpy_b200_substituted = done
+
+
+def pytest_report_header(config):
+    return ["agnpy_b200 substituted for: " + ", ".join(getattr(config, "_agnpy_b200_substituted", []))]
+
+
+def pytest_terminal_summary(terminalreporter):
+    from agnpy_b200 import _lib
+    terminalreporter.write_line(f"agnpy_b200 kernel launches during this session: {_lib.launch_count()}")

@@ -390,3 +390,28 @@ def test_reference_import_paths_and_host_helpers():
     np.testing.assert_allclose(conv.to_R_g_units(1e16 * u.cm, 1e9 * u.M_sun),
                                float(ref_conv.to_R_g_units(1e16 * au.cm, 1e9 * au.M_sun)), rtol=1e-15)
     assert umath.ftiny == ref_math.ftiny and umath.fmax == ref_math.fmax
+
+
+def test_spectra_host_evaluate_and_delta_approximation_match_the_reference():
+    """`n_e(gamma)` / `evaluate` of the five analytic shapes and the closed-form delta approximation of the
+    synchrotron SED (host arithmetic: no integral involved) against the reference's own functions"""
+    from oracle import reference_loader
+    if not reference_loader.available():
+        pytest.skip("needs the reference")
+    agnpy = reference_loader.load()
+    import astropy.units as au
+    g = np.logspace(0.5, 7.5, 60)
+    shapes = [("PowerLaw", (1e-8, 2.3, 10.0, 1e6)), ("BrokenPowerLaw", (1e-8, 2.0, 3.4, 1e4, 20.0, 5e6)),
+              ("LogParabola", (1e-8, 2.1, 0.3, 1e3, 10.0, 1e6)), ("ExpCutoffPowerLaw", (1e-8, 2.0, 1e5, 10.0, 1e7)),
+              ("ExpCutoffBrokenPowerLaw", (1e-8, 1.8, 3.0, 1e5, 1e3, 10.0, 1e7))]
+    for name, args in shapes:
+        mine = getattr(ab, name)(*args)
+        ref = getattr(agnpy, name)(args[0] * au.Unit("cm-3"), *args[1:])
+        want = ref(g.copy()).to_value("cm-3")
+        np.testing.assert_allclose(np.asarray(mine(g)), want, rtol=1e-15, atol=0)
+        assert np.count_nonzero(want) < g.size                      # the box is exercised
+        got = ab.Synchrotron.evaluate_sed_flux_delta_approx(
+            np.logspace(10, 20, 11) * u.Hz, 0.5, 1e27 * u.cm, 10, 1 * u.G, 1e16 * u.cm, mine, *mine.parameters)
+        want = agnpy.Synchrotron.evaluate_sed_flux_delta_approx(
+            np.logspace(10, 20, 11) * au.Hz, 0.5, 1e27 * au.cm, 10, 1 * au.G, 1e16 * au.cm, ref, *ref.parameters)
+        np.testing.assert_allclose(strip(got, "erg cm-2 s-1"), want.to_value("erg cm-2 s-1"), rtol=1e-14, atol=0)

@@ -1,0 +1,40 @@
+"""The reference's OWN test files for the hot path, run with the CUDA classes substituted (gpu).
+
+tests/ref_substitution.py replaces Synchrotron, ProtonSynchrotron, SynchrotronSelfCompton,
+ExternalCompton and Absorption inside the imported, otherwise unmodified reference (agnpy v0.5.0 from
+baseline/_ref) and pytest then collects the reference's test modules as they are: its Blob, spectra,
+targets, literature data files and comparison utilities drive this package's kernels.  Runs in a
+subprocess (the substitution patches module attributes of the imported reference)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+from oracle import reference_loader
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+FILES = ["synchrotron/tests/test_synchrotron.py", "synchrotron/tests/test_proton_synchrotron.py",
+         "compton/tests/test_compton.py", "absorption/tests/test_absorption.py"]
+# not runnable here: the EBL comparison needs gammapy's own EBL models
+NOT_THESE = "not TestEBL"
+
+
+def test_reference_test_files_pass_on_the_cuda_classes():
+    if not reference_loader.available():
+        pytest.skip("the reference install (baseline/_ref) is not here")
+    ref_root = next(c for c in reference_loader.CANDIDATES if (c / "agnpy" / "__init__.py").exists())
+    cmd = [sys.executable, "-m", "pytest", "-p", "tests.ref_substitution", "-q", "-p", "no:cacheprovider",
+           "-W", "ignore", "--rootdir", str(ROOT)]
+    cmd += ["-k", NOT_THESE] + [str(ref_root / "agnpy" / f) for f in FILES]
+    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(res.stdout.splitlines()[-40:])
+    assert res.returncode == 0, f"reference tests on the CUDA classes:\n{tail}\n{res.stderr[-2000:]}"
+    assert " passed" in tail
+    import re
+    launches = re.search(r"agnpy_b200 kernel launches during this session: (\d+)", res.stdout)
+    assert launches and int(launches.group(1)) > 100, "the reference's tests did not reach the CUDA kernels"
+    counts = re.search(r"(\d+) passed", tail)
+    assert counts and int(counts.group(1)) >= 54
