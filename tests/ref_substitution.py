@@ -14,6 +14,7 @@ Everything else the tests touch stays the reference's own: Blob, the spectra cla
 normalisation class methods, the targets, the literature data files, the comparison utilities -- the scenario
 of INTEGRATION.md, where a maintainer keeps the package and swaps the numpy bodies for the C ABI.
 Test infrastructure: used by tests/test_reference_suite_on_cuda.py (gpu)."""
+import os
 import sys
 from pathlib import Path
 
@@ -28,11 +29,15 @@ SUBSTITUTED = {
     "agnpy.compton": ("SynchrotronSelfCompton", "ExternalCompton"),
     "agnpy.absorption": ("Absorption",),
 }
+if os.environ.get("AGNPY_B200_SUBSTITUTE_TARGETS") == "1":   # the "next" row: u(r), black-body SEDs
+    SUBSTITUTED["agnpy.targets"] = ("CMB", "PointSourceBehindJet", "SSDisk", "SphericalShellBLR", "RingDustTorus")
 # the module files that define the classes inside those packages
 _INNER = {
     "Synchrotron": "agnpy.synchrotron.synchrotron", "ProtonSynchrotron": "agnpy.synchrotron.proton_synchrotron",
     "SynchrotronSelfCompton": "agnpy.compton.synchrotron_self_compton",
     "ExternalCompton": "agnpy.compton.external_compton", "Absorption": "agnpy.absorption.targets_absorption",
+    "CMB": "agnpy.targets.targets", "PointSourceBehindJet": "agnpy.targets.targets", "SSDisk": "agnpy.targets.targets",
+    "SphericalShellBLR": "agnpy.targets.targets", "RingDustTorus": "agnpy.targets.targets",
 }
 
 
