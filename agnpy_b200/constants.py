@@ -9,6 +9,7 @@ e = 4.803204712570263e-10
 sigma_T = 6.6524587321e-25
 G = 6.6743e-8
 k_B = 1.380649e-16
+sigma_sb = 5.670374419e-5   # astropy's (CODATA 2018) Stefan-Boltzmann constant in erg cm-2 s-1 K-4
 M_sun = 1.988409870698051e33
 mec2 = m_e * c**2
 lambda_c_e = h / (m_e * c)

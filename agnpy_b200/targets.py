@@ -11,9 +11,51 @@ from .units import strip, u, wrap
 __all__ = ["CMB", "PointSourceBehindJet", "SSDisk", "SphericalShellBLR", "RingDustTorus",
            "Blob", "lines_dictionary"]
 
-# rest wavelengths [Angstrom] of a few broad lines (Finke 2016, table 5)
-lines_dictionary = {"Lyalpha": 1215.67, "Lybeta": 1025.72, "CIV": 1549.06, "MgII": 2797.92,
-                    "Hbeta": 4861.33, "Halpha": 6562.80}
+# broad emission lines of the stratified BLR model (Finke 2016, table 5; the reference's
+# targets.py:22-150 holds the same published numbers)
+_LINES = (  # name, rest wavelength [Angstrom], R_line / R_Hbeta, L_line / L_Hbeta
+    ('Lyepsilon', 937.8, 2.7, 0.24),
+    ('Lydelta', 949.74, 2.8, 0.24),
+    ('CIII', 977.02, 0.83, 0.6),
+    ('NIII', 990.69, 0.85, 0.6),
+    ('Lybeta', 1025.72, 1.2, 1.1),
+    ('OVI', 1033.83, 1.2, 1.1),
+    ('ArI', 1066.66, 4.5, 0.094),
+    ('Lyalpha', 1215.67, 0.27, 12),
+    ('OI', 1304.35, 4.0, 0.23),
+    ('SiII', 1306.82, 4.0, 0.23),
+    ('SiIV', 1396.76, 0.83, 1.0),
+    ('OIV]', 1402.06, 0.83, 1.0),
+    ('CIV', 1549.06, 0.83, 2.9),
+    ('NIV', 1718.55, 3.8, 0.3),
+    ('AlII', 1721.89, 3.8, 0.3),
+    ('CIII]', 1908.73, 0.46, 1.8),
+    ('[NeIV]', 2423.83, 5.8, 0.051),
+    ('MgII', 2798.75, 0.45, 1.7),
+    ('Hdelta', 4102.89, 3.4, 0.12),
+    ('Hgamma', 4341.68, 3.2, 0.3),
+    ('HeII', 4687.02, 0.63, 0.016),
+    ('Hbeta', 4862.68, 1.0, 1.0),
+    ('[ClIII]', 5539.43, 4.8, 0.039),
+    ('HeI', 5877.29, 0.39, 0.092),
+    ('Halpha', 6564.61, 1.3, 3.6),
+)
+
+
+class _LineDictionary(dict):
+    """`lines_dictionary[name]` -> {"lambda": Quantity [Angstrom], "R_Hbeta_ratio", "L_Hbeta_ratio"} as in
+    the reference; the wavelength is wrapped on access so that it follows the active units module"""
+
+    def __getitem__(self, name):
+        lam, r_ratio, l_ratio = dict.__getitem__(self, name)
+        return {"lambda": wrap(lam, "Angstrom"), "R_Hbeta_ratio": r_ratio, "L_Hbeta_ratio": l_ratio}
+
+    def wavelength(self, name):
+        """rest wavelength in Angstrom as a plain number"""
+        return dict.__getitem__(self, name)[0]
+
+
+lines_dictionary = _LineDictionary({name: (lam, r, l) for name, lam, r, l in _LINES})
 
 
 def _d_L_of(z, d_L=None, cosmology=None):
@@ -43,7 +85,8 @@ class CMB:
 
     def __init__(self, z):
         T = 2.72548
-        self.u_0 = (7.5657 * 1e-15 * np.power(T, 4)) * np.power(1 + z, 4) * u.Unit("erg cm-3")
+        self.T, self.z = wrap(T, "K"), z
+        self.u_0 = wrap((7.5657 * 1e-15 * np.power(T, 4)) * np.power(1 + z, 4), "erg cm-3")
         self.epsilon_0 = (2.7 * const.k_B * T / const.mec2) * (1 + z)
 
     def u(self, blob=None):
@@ -68,18 +111,77 @@ class SSDisk:
     """targets.py:221-276"""
 
     def __init__(self, M_BH, L_disk, eta, R_in, R_out, R_g_units=False):
+        self.name = "Shakura Sunyaev Accretion Disk"
         self.M_BH, self.L_disk, self.eta = M_BH, L_disk, eta
-        R_g = const.G * strip(M_BH, "g", "M_BH") / const.c**2
-        self.R_g = R_g * u.cm
-        if R_g_units:
-            self.R_in_tilde, self.R_out_tilde = float(R_in), float(R_out)
-            self.R_in, self.R_out = R_in * R_g * u.cm, R_out * R_g * u.cm
-        else:
+        M, L = strip(M_BH, "g", "M_BH"), strip(L_disk, "erg s-1", "L_disk")
+        # targets.py:240-248: Eddington luminosity 1.26e46 M_8 erg/s, accretion rate L / (eta c^2)
+        self.M_8 = M / (1e8 * const.M_sun)
+        self.L_Edd = wrap(1.26 * 1e46 * self.M_8, "erg s-1")
+        self.l_Edd = L / (1.26 * 1e46 * self.M_8)
+        self.m_dot = wrap(L / (eta * const.c**2), "g s-1")
+        R_g = const.G * M / const.c**2
+        self.R_g = wrap(R_g, "cm")
+        numbers = (int, float, np.integer, np.floating)
+        if R_g_units:      # targets.py:251-260: plain numbers in units of R_g
+            if not isinstance(R_in, numbers) or not isinstance(R_out, numbers):
+                raise TypeError("R_in / R_out passed with units, int / float expected")
+            self.R_in_tilde, self.R_out_tilde = R_in, R_out
+            self.R_in, self.R_out = wrap(R_in * R_g, "cm"), wrap(R_out * R_g, "cm")
+        else:              # targets.py:261-271: quantities
+            if not hasattr(R_in, "to_value") or not hasattr(R_out, "to_value"):
+                raise TypeError("R_in / R_out passed without units")
             self.R_in, self.R_out = R_in, R_out
             self.R_in_tilde = strip(R_in, "cm", "R_in") / R_g
             self.R_out_tilde = strip(R_out, "cm", "R_out") / R_g
-        # targets.py:247-248: m_dot = L_disk / (eta c^2)
-        self.m_dot = strip(L_disk, "erg s-1", "L_disk") / (eta * const.c**2) * u.Unit("g s-1")
+        self.R_tilde = np.linspace(self.R_in_tilde, self.R_out_tilde)
+
+    # ---- small host helpers of the reference's class (targets.py:289-348), used by its callers and tests
+    @staticmethod
+    def evaluate_mu_from_r_tilde(R_in_tilde, R_out_tilde, r_tilde, size=100):
+        """cosines under which the disk is seen from the height r_tilde (Finke 2016, eqs. 72-73)"""
+        mu_min = 1 / np.sqrt(1 + np.power(R_out_tilde / r_tilde, 2))
+        mu_max = 1 / np.sqrt(1 + np.power(R_in_tilde / r_tilde, 2))
+        return np.linspace(mu_min, mu_max, size)
+
+    @staticmethod
+    def evaluate_phi_disk_mu(mu, R_in_tilde, r_tilde):
+        """1 - sqrt(R_in / R) at the radius seen under the cosine mu (Dermer 2009, eq. 63)"""
+        return 1 - np.sqrt(R_in_tilde / (r_tilde * np.sqrt(np.power(mu, -2) - 1)))
+
+    @staticmethod
+    def evaluate_epsilon(L_disk, M_BH, eta, R_tilde):
+        """dimensionless energy of the photons emitted at R_tilde (Dermer 2009, eq. 65)"""
+        M_8 = strip(M_BH, "g", "M_BH") / (1e8 * const.M_sun)
+        l_Edd = strip(L_disk, "erg s-1", "L_disk") / (1.26 * 1e46 * M_8)
+        return 2.7 * 1e-4 * np.power(l_Edd / (M_8 * eta), 1 / 4) * np.power(R_tilde, -3 / 4)
+
+    @staticmethod
+    def evaluate_epsilon_mu(L_disk, M_BH, eta, mu, r_tilde):
+        return SSDisk.evaluate_epsilon(L_disk, M_BH, eta, r_tilde * np.sqrt(np.power(mu, -2) - 1))
+
+    @staticmethod
+    def evaluate_T(R, M_BH, m_dot, R_in):
+        """disk temperature at the radius R (Dermer 2009, eq. 64)"""
+        R_cm, Rin = strip(R, "cm", "R"), strip(R_in, "cm", "R_in")
+        phi = 1 - np.sqrt(Rin / R_cm)
+        val = (3 * const.G * strip(M_BH, "g", "M_BH") * strip(m_dot, "g s-1", "m_dot") * phi) / (
+            8 * np.pi * np.power(R_cm, 3) * const.sigma_sb)
+        return wrap(np.power(val, 1 / 4), "K")
+
+    def epsilon_mu(self, mu, r_tilde):
+        return self.evaluate_epsilon_mu(self.L_disk, self.M_BH, self.eta, mu, r_tilde)
+
+    def epsilon(self, R_tilde):
+        return self.evaluate_epsilon(self.L_disk, self.M_BH, self.eta, R_tilde)
+
+    def phi_disk_mu(self, mu, r_tilde):
+        return self.evaluate_phi_disk_mu(mu, self.R_in_tilde, r_tilde)
+
+    def phi_disk(self, R_tilde):
+        return 1 - np.sqrt(self.R_in_tilde / R_tilde)
+
+    def T(self, R):
+        return self.evaluate_T(R, self.M_BH, self.m_dot, self.R_in)
 
     @staticmethod
     def _bb(variant, nu, z, M_BH, m_dot, R_in, R_out, d_L, mu_s, L_disk=None):
@@ -123,8 +225,8 @@ class SphericalShellBLR:
         if line not in lines_dictionary:
             raise NameError(f"{line} not available in the line dictionary")
         self.L_disk, self.xi_line, self.line, self.R_line = L_disk, xi_line, line, R_line
-        self.lambda_line = lines_dictionary[line] * u.Unit("Angstrom")
-        lam_cm = lines_dictionary[line] * 1e-8
+        self.lambda_line = wrap(lines_dictionary.wavelength(line), "Angstrom")
+        lam_cm = lines_dictionary.wavelength(line) * 1e-8
         self.epsilon_line = const.h * const.c / lam_cm / const.mec2
 
     def u(self, r, blob=None):
@@ -144,7 +246,7 @@ class RingDustTorus:
         self.epsilon_dt = 2.7 * self.Theta
         if R_dt is None:
             L = strip(L_disk, "erg s-1", "L_disk")
-            self.R_dt = 3.5 * 1e18 * np.sqrt(L / 1e45) * np.power(T / 1e3, -2.6) * u.cm
+            self.R_dt = wrap(3.5 * 1e18 * np.sqrt(L / 1e45) * np.power(T / 1e3, -2.6), "cm")
         else:
             self.R_dt = R_dt
 
@@ -172,7 +274,7 @@ class RingDustTorus:
     def sed_flux(self, nu, z, d_L=None):
         """targets.py:612-618; d_L = Distance(z) (Planck18) unless given"""
         d_L = _d_L_of(z, d_L)
-        L_dt = self.xi_dt * strip(self.L_disk, "erg s-1", "L_disk") * u.Unit("erg s-1")
+        L_dt = wrap(self.xi_dt * strip(self.L_disk, "erg s-1", "L_disk"), "erg s-1")
         return self.evaluate_bb_norm_sed(nu, z, L_dt, self.T_dt, self.R_dt, d_L)
 
     def u(self, r, blob=None):

@@ -18,23 +18,38 @@ ROOT = Path(__file__).resolve().parents[1]
 
 FILES = ["synchrotron/tests/test_synchrotron.py", "synchrotron/tests/test_proton_synchrotron.py",
          "compton/tests/test_compton.py", "absorption/tests/test_absorption.py"]
+TARGET_FILES = ["targets/tests/test_targets.py"]
 # not runnable here: the EBL comparison needs gammapy's own EBL models
 NOT_THESE = "not TestEBL"
 
 
-def test_reference_test_files_pass_on_the_cuda_classes():
-    if not reference_loader.available():
-        pytest.skip("the reference install (baseline/_ref) is not here")
+def _run(files, targets_too):
+    import os
+    import re
     ref_root = next(c for c in reference_loader.CANDIDATES if (c / "agnpy" / "__init__.py").exists())
     cmd = [sys.executable, "-m", "pytest", "-p", "tests.ref_substitution", "-q", "-p", "no:cacheprovider",
-           "-W", "ignore", "--rootdir", str(ROOT)]
-    cmd += ["-k", NOT_THESE] + [str(ref_root / "agnpy" / f) for f in FILES]
-    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+           "-W", "ignore", "--rootdir", str(ROOT), "-k", NOT_THESE]
+    cmd += [str(ref_root / "agnpy" / f) for f in files]
+    env = dict(os.environ, AGNPY_B200_SUBSTITUTE_TARGETS="1" if targets_too else "0")
+    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500, env=env)
     tail = "\n".join(res.stdout.splitlines()[-40:])
     assert res.returncode == 0, f"reference tests on the CUDA classes:\n{tail}\n{res.stderr[-2000:]}"
-    assert " passed" in tail
-    import re
     launches = re.search(r"agnpy_b200 kernel launches during this session: (\d+)", res.stdout)
     assert launches and int(launches.group(1)) > 100, "the reference's tests did not reach the CUDA kernels"
-    counts = re.search(r"(\d+) passed", tail)
-    assert counts and int(counts.group(1)) >= 54
+    return int(re.search(r"(\d+) passed", tail).group(1))
+
+
+def test_reference_test_files_pass_on_the_cuda_classes():
+    """Synchrotron, ProtonSynchrotron, SynchrotronSelfCompton, ExternalCompton, Absorption substituted; the
+    reference's Blob, spectra and targets drive them"""
+    if not reference_loader.available():
+        pytest.skip("the reference install (baseline/_ref) is not here")
+    assert _run(FILES, targets_too=False) >= 54
+
+
+def test_reference_test_files_pass_with_the_target_classes_substituted_too():
+    """in addition CMB, PointSourceBehindJet, SSDisk, SphericalShellBLR, RingDustTorus (u(r), black-body
+    SEDs, the container helpers) and the reference's own target tests"""
+    if not reference_loader.available():
+        pytest.skip("the reference install (baseline/_ref) is not here")
+    assert _run(TARGET_FILES + FILES, targets_too=True) >= 96
