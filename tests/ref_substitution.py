@@ -52,6 +52,10 @@ def substitute():
     import astropy.units as au
     bu._astropy_units, bu.HAVE_ASTROPY = au, True
     done = []
+    # the log-log integrator as a callable (utils/math.py:55-119): evaluated on the device
+    ref_math = importlib.import_module("agnpy.utils.math")
+    ref_math.trapz_loglog = ab.trapz_loglog
+    done.append("agnpy.utils.math.trapz_loglog")
     for pkg, names in SUBSTITUTED.items():
         mod = importlib.import_module(pkg)
         for name in names:

@@ -17,10 +17,11 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 FILES = ["synchrotron/tests/test_synchrotron.py", "synchrotron/tests/test_proton_synchrotron.py",
-         "compton/tests/test_compton.py", "absorption/tests/test_absorption.py"]
+         "compton/tests/test_compton.py", "absorption/tests/test_absorption.py", "utils/tests/test_utils.py"]
 TARGET_FILES = ["targets/tests/test_targets.py"]
-# not runnable here: the EBL comparison needs gammapy's own EBL models
-NOT_THESE = "not TestEBL"
+# not runnable here: the EBL comparison needs gammapy's own EBL models; of utils/tests/test_utils.py only the
+# trapz_loglog test involves this package (the rest tests the reference's own geometry helpers and plots)
+NOT_THESE = "not TestEBL and (trapz_log_log or not test_utils)"
 
 
 def _run(files, targets_too):
@@ -44,7 +45,7 @@ def test_reference_test_files_pass_on_the_cuda_classes():
     reference's Blob, spectra and targets drive them"""
     if not reference_loader.available():
         pytest.skip("the reference install (baseline/_ref) is not here")
-    assert _run(FILES, targets_too=False) >= 54
+    assert _run(FILES, targets_too=False) >= 54 + 81
 
 
 def test_reference_test_files_pass_with_the_target_classes_substituted_too():
@@ -52,4 +53,4 @@ def test_reference_test_files_pass_with_the_target_classes_substituted_too():
     SEDs, the container helpers) and the reference's own target tests"""
     if not reference_loader.available():
         pytest.skip("the reference install (baseline/_ref) is not here")
-    assert _run(TARGET_FILES + FILES, targets_too=True) >= 96
+    assert _run(TARGET_FILES + FILES, targets_too=True) >= 96 + 81
