@@ -169,7 +169,14 @@ def snap_boundaries(gamma, gamma_min, gamma_max):
 def describe(n_e, args):
     """(n_e object, *args) of an evaluate_* call -> (kind, 8 doubles).  `args` follow the
     reference's `parameters` order; `k` may be a Quantity [cm-3]."""
-    name = type(n_e).__name__ if not isinstance(n_e, str) else n_e
+    # an instance, the class itself (the reference only calls the static `n_e.evaluate`, and its fit
+    # wrappers pass the class: sherpa_wrapper.py:66-75), or the name
+    if isinstance(n_e, str):
+        name = n_e
+    elif isinstance(n_e, type):
+        name = n_e.__name__
+    else:
+        name = type(n_e).__name__
     if name not in _KINDS:
         name = getattr(n_e, "tag", name)
     if name not in _KINDS:

@@ -13,7 +13,8 @@ package namespaces before the reference's test modules are collected:
 Everything else the tests touch stays the reference's own: Blob, the spectra classes and their
 normalisation class methods, the targets, the literature data files, the comparison utilities -- the scenario
 of INTEGRATION.md, where a maintainer keeps the package and swaps the numpy bodies for the C ABI.
-Test infrastructure: used by tests/test_reference_suite_on_cuda.py (gpu)."""
+`python -m tests.ref_substitution` runs the cases of tests/ref_cases.py the same way (run_reference_cases) and
+prints one line per case.  Test infrastructure: used by tests/test_reference_suite_on_cuda.py (gpu)."""
 import os
 import sys
 from pathlib import Path
@@ -64,7 +65,40 @@ def substitute():
                 if hasattr(target, name):
                     setattr(target, name, cuda_cls)
             done.append(f"{pkg}.{name}")
+    # the fit wrappers imported the compute classes by name: the reference's own sherpa / gammapy wrapper
+    # code then drives the CUDA classes (targets stay whatever the packages above hold)
+    for wrapper in ("agnpy.fit.sherpa_wrapper", "agnpy.fit.gammapy_wrapper"):
+        try:
+            w = importlib.import_module(wrapper)
+        except Exception:      # needs the sherpa / gammapy shells of the test infrastructure
+            continue
+        for names in SUBSTITUTED.values():
+            for name in names:
+                if hasattr(w, name):
+                    setattr(w, name, getattr(ab, name))
+        done.append(wrapper)
     return done
+
+
+def run_reference_cases(names=None):
+    """every case of tests/ref_cases.py through the REFERENCE side of the case code -- the reference's Blob,
+    spectra, targets, fit wrappers and (stand-in) astropy Quantities -- with the CUDA classes substituted,
+    against the fixtures the unmodified reference produced: {case: (max rel dev, zeros agree)}"""
+    import numpy as np
+
+    from agnpy_b200 import _lib
+    from tests import cases, ref_cases
+    agnpy = reference_loader.load()
+    substitute()
+    store = dict(np.load(cases.GOLDEN / "ref_evaluate.npz"))
+    store.pop("__meta__", None)
+    A = ref_cases.RefSide(agnpy)
+    out = {}
+    for name in (names or ref_cases.CASES):
+        with _lib.strict_reference_mode("_ssa" in name), np.errstate(all="ignore"):
+            got = np.asarray(ref_cases.run(name, "ref", A, dict(store)), dtype=np.float64)
+        out[name] = cases.max_rel_dev(got, store[name])
+    return out
 
 
 def pytest_configure(config):
@@ -79,3 +113,16 @@ def pytest_report_header(config):
 def pytest_terminal_summary(terminalreporter):
     from agnpy_b200 import _lib
     terminalreporter.write_line(f"agnpy_b200 kernel launches during this session: {_lib.launch_count()}")
+
+
+if __name__ == "__main__":
+    import warnings
+    warnings.simplefilter("ignore")
+    res = run_reference_cases(sys.argv[1:] or None)
+    from agnpy_b200 import _lib
+    worst = 0.0
+    for name, (dev, zeros_ok) in res.items():
+        worst = max(worst, dev)
+        print(f"{name:36s} {dev:10.2e} {'zeros ok' if zeros_ok else 'ZEROS DIFFER'}")
+    print(f"# {len(res)} cases through the reference's own calling code on the CUDA classes: max deviation "
+          f"{worst:.2e}, {_lib.launch_count()} kernel launches")

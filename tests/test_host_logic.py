@@ -87,6 +87,12 @@ def test_spectra_describe_follows_reference_parameter_order():
     class PowerLaw:  # an object of the reference's own class is recognised by name
         tag = "PowerLaw"
     assert spectra.describe(PowerLaw(), [1e-7, 2.1, 10, 1e5])[0] == _lib.NE_POWERLAW
+    import abc
+
+    class LogParabola(metaclass=abc.ABCMeta):   # ... and so is the class itself (the reference's fit wrappers
+        pass                                    # pass the class: only the static `evaluate` is ever called)
+    assert spectra.describe(LogParabola, [1e-7, 2.1, 0.2, 1e3, 10, 1e5])[0] == _lib.NE_LOG_PARABOLA
+    assert spectra.describe(spectra.BrokenPowerLaw, [1e-7, 2.1, 3.0, 1e3, 10, 1e5])[0] == _lib.NE_BROKEN_POWERLAW
     with pytest.raises(ValueError):
         spectra.describe(PowerLaw(), [1e-7, 2.1, 10])
     with pytest.raises(TypeError):

@@ -54,3 +54,21 @@ def test_reference_test_files_pass_with_the_target_classes_substituted_too():
     if not reference_loader.available():
         pytest.skip("the reference install (baseline/_ref) is not here")
     assert _run(TARGET_FILES + FILES, targets_too=True) >= 96 + 81
+
+
+def test_reference_calling_code_on_the_cuda_classes_reproduces_the_fixtures():
+    """every case of tests/ref_cases.py through the REFERENCE side of the case code -- the reference's Blob,
+    spectra classes (passed as classes, as its fit wrappers do), targets, sherpa / gammapy wrapper functions
+    and Quantities -- with the CUDA classes substituted: the outputs must be those the unmodified reference
+    produced (tests/golden/ref_evaluate.npz) at 1e-9"""
+    if not reference_loader.available():
+        pytest.skip("the reference install (baseline/_ref) is not here")
+    res = subprocess.run([sys.executable, "-m", "tests.ref_substitution"], cwd=ROOT, capture_output=True,
+                         text=True, timeout=1500)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    lines = [ln.split() for ln in res.stdout.splitlines() if ln and not ln.startswith("#")]
+    assert len(lines) >= 60
+    for name, dev, *flag in lines:
+        assert flag[:2] == ["zeros", "ok"], f"{name}: exact zeros differ"
+        assert float(dev) <= 1e-9, f"{name}: {dev}"
+    assert any(name.startswith("fit_sherpa") for name, *_ in lines)
