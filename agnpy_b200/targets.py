@@ -89,6 +89,10 @@ class CMB:
         self.u_0 = wrap((7.5657 * 1e-15 * np.power(T, 4)) * np.power(1 + z, 4), "erg cm-3")
         self.epsilon_0 = (2.7 * const.k_B * T / const.mec2) * (1 + z)
 
+    def __str__(self):
+        return f"* CMB radiation field at z = {self.z}: u_0 = {strip(self.u_0, 'erg cm-3'):.2e} erg cm-3, " \
+               f"epsilon_0 = {self.epsilon_0:.2e}"
+
     def u(self, blob=None):
         """targets.py:171-183 (two flops: evaluated on the host)"""
         if blob:
@@ -101,6 +105,10 @@ class PointSourceBehindJet:
 
     def __init__(self, L_0, epsilon_0):
         self.L_0, self.epsilon_0 = L_0, epsilon_0
+
+    def __str__(self):
+        return f"* point source behind the jet: L_0 = {strip(self.L_0, 'erg s-1'):.2e} erg s-1, " \
+               f"epsilon_0 = {self.epsilon_0:.2e}"
 
     def u(self, r, blob=None):
         """targets.py:202-218"""
@@ -134,6 +142,12 @@ class SSDisk:
             self.R_in_tilde = strip(R_in, "cm", "R_in") / R_g
             self.R_out_tilde = strip(R_out, "cm", "R_out") / R_g
         self.R_tilde = np.linspace(self.R_in_tilde, self.R_out_tilde)
+
+    def __str__(self):
+        return (f"* Shakura-Sunyaev accretion disk: M_BH = {strip(self.M_BH, 'g'):.2e} g, "
+                f"L_disk = {strip(self.L_disk, 'erg s-1'):.2e} erg s-1, eta = {self.eta:.2e}, "
+                f"m_dot = {strip(self.m_dot, 'g s-1'):.2e} g s-1, R_in = {strip(self.R_in, 'cm'):.2e} cm, "
+                f"R_out = {strip(self.R_out, 'cm'):.2e} cm")
 
     # ---- small host helpers of the reference's class (targets.py:289-348), used by its callers and tests
     @staticmethod
@@ -229,6 +243,11 @@ class SphericalShellBLR:
         lam_cm = lines_dictionary.wavelength(line) * 1e-8
         self.epsilon_line = const.h * const.c / lam_cm / const.mec2
 
+    def __str__(self):
+        return (f"* spherical-shell broad line region: L_disk = {strip(self.L_disk, 'erg s-1'):.2e} erg s-1, "
+                f"xi_line = {self.xi_line:.2e}, line = {self.line} "
+                f"({strip(self.lambda_line, 'Angstrom'):.2f} Angstrom), R_line = {strip(self.R_line, 'cm'):.2e} cm")
+
     def u(self, r, blob=None):
         """targets.py:516-543"""
         tgt = [strip(self.L_disk, "erg s-1", "L_disk"), float(self.xi_line), self.epsilon_line,
@@ -249,6 +268,10 @@ class RingDustTorus:
             self.R_dt = wrap(3.5 * 1e18 * np.sqrt(L / 1e45) * np.power(T / 1e3, -2.6), "cm")
         else:
             self.R_dt = R_dt
+
+    def __str__(self):
+        return (f"* ring dust torus: L_disk = {strip(self.L_disk, 'erg s-1'):.2e} erg s-1, xi_dt = {self.xi_dt:.2e}, "
+                f"T_dt = {strip(self.T_dt, 'K'):.2e} K, R_dt = {strip(self.R_dt, 'cm'):.2e} cm")
 
     @staticmethod
     def _bb(variant, nu, z, T_dt, R_dt, d_L, L_dt=None):

@@ -72,3 +72,20 @@ def test_reference_calling_code_on_the_cuda_classes_reproduces_the_fixtures():
         assert flag[:2] == ["zeros", "ok"], f"{name}: exact zeros differ"
         assert float(dev) <= 1e-9, f"{name}: {dev}"
     assert any(name.startswith("fit_sherpa") for name, *_ in lines)
+
+
+def test_reference_documentation_snippets_run_on_the_cuda_classes():
+    """docs/snippets/{blob,synchro,ssc,ec,absorption,targets,p_synchro}_snippet.py of the reference -- the
+    usage its documentation shows -- executed unchanged with the compute and target classes substituted"""
+    if not reference_loader.available():
+        pytest.skip("the reference install (baseline/_ref) is not here")
+    ref_root = next(c for c in reference_loader.CANDIDATES if (c / "agnpy" / "__init__.py").exists())
+    if not (ref_root / "docs" / "snippets" / "ec_snippet.py").exists():
+        pytest.skip("the documentation snippets are not part of this reference install")
+    res = subprocess.run([sys.executable, "-m", "tests.run_reference_snippets"], cwd=ROOT, capture_output=True,
+                         text=True, timeout=1500)
+    ran = [ln for ln in res.stdout.splitlines() if ln.startswith("SNIPPET")]
+    assert res.returncode == 0 and len(ran) == 7 and all(" ran, " in ln for ln in ran), \
+        "\n".join(ran) + res.stderr[-3000:]
+    launches = {ln.split()[1]: int(ln.split()[3]) for ln in ran}
+    assert all(launches[k] > 0 for k in ("synchro_snippet", "ssc_snippet", "ec_snippet", "absorption_snippet"))
